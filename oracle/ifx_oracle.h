@@ -1,0 +1,109 @@
+/*
+ * ifx_oracle.h — CPU restatement of the ImmerseFlow++ fractional-step hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under oracle/ is part of the product: only tests/,
+ * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load
+ * libifx_oracle.so, and only as the checker / reported CPU baseline.  The product
+ * (immerseflow_b200/) never links, imports or falls back to this code.
+ *
+ * Every function cites the reference file:line (relative to /root/reference) it restates.
+ * Arithmetic follows the reference CUDA build bit for bit: the FMA contractions that
+ * nvcc 12.9 (-arch=sm_100, default -fmad=true) emits for each expression were read from
+ * the reference's PTX + SASS and are written out with explicit fma(); the file is compiled
+ * with -ffp-contract=off so the C compiler adds none of its own.
+ *
+ * Parity status:
+ *   PINNED   (golden files results/{uc,vc,p,final_results}.dat reproduce exactly at 6
+ *             decimals — tests/test_oracle_golden.py): grid metrics, IC, predictor
+ *             (ADsolver), reduction order, Laplace-Jacobi PPE as written.
+ *   UNPINNED (no reference code exists; this oracle DEFINES the semantics — see
+ *             ifx_oracle_full.c): PPE source term, Neumann pressure BC, projection,
+ *             iBlank classification of real bodies, ghost-cell image-point interpolation.
+ */
+#ifndef IFX_ORACLE_H
+#define IFX_ORACLE_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- a2: grid metrics, preSim.cu:294-355 --------------------------------------------- */
+void orc_grid_metrics(int nx, int ny, const double* xf, const double* yf,
+                      double* xc, double* yc, double* dx2d, double* dy2d);
+
+/* ---- a19: initial condition, preSim.cu:53-97 ----------------------------------------- */
+void orc_initializeKernel(int nx, int ny, const double* xc, const double* yc,
+                          double* u, double* v, double* p);
+
+/* ---- a16 (as written): iBlank == 1.0 everywhere, preSim.cu:110-136 --------------------- */
+void orc_iBlankComputeKernel(int nx, int ny, const double* xc, const double* yc, double* iblank);
+
+/* ---- a3: ADSolver.cu:12-44 ----------------------------------------------------------- */
+void orc_calculateADCoefficients(int nx, int ny, const double* dx, const double* dy,
+                                 double dt, double Re,
+                                 double* coeff, double* dx2_m1, double* dx2_p1,
+                                 double* dy2_m1, double* dy2_p1);
+
+/* ---- a4: ADSolver.cu:162-189.  vf_mode 0 = as written (second loop only runs for thread ids
+ *      in [(nx-1)(ny-2), (nx-2)(ny-1)); empty when nx <= ny), 1 = as intended (all vf). ----- */
+void orc_Compute_velf(int nx, int ny, const double* dx, const double* dy,
+                      const double* u, const double* v, double* uf, double* vf, int vf_mode);
+
+/* ---- a5: ADSolver.cu:191-219 (cell-centre part; the face loops :221-263 never execute) --- */
+void orc_set_velocity_BC(int nx, int ny, double* u, double* v);
+
+/* ---- a6: ADSolver.cu:46-79 ----------------------------------------------------------- */
+void orc_ADSource(int nx, int ny, const double* dx, const double* dy, double dt,
+                  const double* u, const double* v, const double* uf, const double* vf,
+                  double* sx, double* sy);
+
+/* ---- a7: ADSolver.cu:81-120 (one kernel serves u and v: identical arithmetic) ---------- */
+void orc_ADsolver_kernel(int nx, int ny,
+                         const double* coeff, const double* dx2_m1, const double* dx2_p1,
+                         const double* dy2_m1, const double* dy2_p1, const double* iblank,
+                         const double* q, double* qnew, const double* s);
+
+/* ---- a8: ADSolver.cu:122-160 ---------------------------------------------------------- */
+void orc_Compute_Residual_AD(int nx, int ny, const double* iblank,
+                             const double* q, const double* qnew, double* res);
+
+/* ---- a9: preSim.cu:12-50 + :376-441, bit-faithful summation order --------------------- */
+double orc_Reduction(const double* in, int n, int threadsPerBlock, int blocksPerGrid);
+
+/* ---- a10: one predictor time step, ADSolver.cu:268-395.  u,v are updated in place (the
+ *      reference's pointer swap is emulated internally; utmp/vtmp are the per-step
+ *      temporaries whose ghost ring, like a fresh cudaMalloc, is never initialised by
+ *      the solver — see K==1 note in the .c file).  Returns the iteration count K;
+ *      res_hist receives (uRes,vRes) per iteration, 2*K doubles. -------------------------- */
+int orc_ADsolver(int nx, int ny, const double* dx, const double* dy, double dt, double Re,
+                 int AD_itermax, const double* iblank,
+                 double* u, double* v, double* uf, double* vf,
+                 int vf_mode, double* res_hist);
+
+/* ---- a11-a14: Laplace-Jacobi PPE as written, PPESolver.cu:13-104,137-197 ---------------- */
+void orc_calculatePPECoefficients(int nx, int ny, const double* dx, const double* dy,
+                                  double* coeff_ppe, double* dx2_m1, double* dx2_p1,
+                                  double* dy2_m1, double* dy2_p1);
+void orc_set_pressure_BC(int nx, int ny, double* p);
+void orc_jacobiIteration(int nx, int ny,
+                         const double* coeff_ppe, const double* dx2_m1, const double* dx2_p1,
+                         const double* dy2_m1, const double* dy2_p1,
+                         const double* p, double* p_new);
+void orc_Compute_Residual(int nx, int ny,
+                          const double* coeff_ppe, const double* dx2_m1, const double* dx2_p1,
+                          const double* dy2_m1, const double* dy2_p1,
+                          const double* p, double* residual);
+/* Returns the sweep count; p updated in place; *final_residual = last signed sum. */
+int orc_PPESolver(int nx, int ny, const double* dx, const double* dy,
+                  int PPE_itermax, double* p, double* final_residual);
+
+/* ---- b: Tecplot writer, postSim.cu:41-66 ---------------------------------------------- */
+int orc_write_results_to_file(const double* x, const double* y, const double* data,
+                              int ni, int nj, const char* filename);
+
+int orc_num_threads(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
