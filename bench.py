@@ -1,0 +1,271 @@
+#!/usr/bin/env python
+"""bench.py — Mcell-steps/s of the fractional-step hot path on N B200s (BASELINE.json's metric).
+
+    python bench.py --gpus 1 --steps K --warmup W             # our CUDA path
+    python bench.py --impl reference ...                      # CPU arm: OpenMP transcription of the reference loops
+    torchrun --nproc-per-node N bench.py --gpus N ...         # slab-decomposed, one rank per GPU
+
+A "step" is one pass of the hot path over the whole grid: predictor (source + Jacobi iterations to the
+reference's stop rule / AD_itermax) followed by the Poisson solve (sweeps to the stop rule / PPE_itermax) and, in
+full mode, the projection.  Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "Mcell-steps/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=6)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--nx", type=int, default=16384, help="cells in x (workload: 16384x16384, north_star's scaling grid)")
+    ap.add_argument("--ny", type=int, default=16384)
+    ap.add_argument("--ad-itermax", type=int, default=25, help="AD_itermax of the shipped inputs.txt")
+    ap.add_argument("--ppe-sweeps", type=int, default=50, help="PPE_itermax for the bench step (bounded Poisson solve)")
+    ap.add_argument("--dt", type=float, default=1e-3)
+    ap.add_argument("--Re", type=float, default=150.0)
+    ap.add_argument("--cpu-sample-rows", type=int, default=192, help="rows of the workload the CPU baseline runs on")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            f = tempfile.NamedTemporaryFile(prefix="ifx_clocks_", suffix=".csv", delete=False)
+            self.path = f.name
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self) -> dict:
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if not self.proc:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                c = [x.strip() for x in line.split(",")]
+                if len(c) < 9:
+                    continue
+                try:
+                    sm.append(float(c[1])); mx.append(float(c[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            # median over the samples under load (top half), the idle ones before/after are not the kernel's clocks
+            s = sorted(sm)
+            out["sm_mhz"] = float(np.median(s[len(s) // 2:]))
+            out["sm_max_mhz"] = max(mx)
+            out["samples"] = len(sm)
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_arm(args, rows: int, steps: int, warmup: int):
+    """The reference has no CPU path; its reported CPU baseline is the OpenMP transcription of its loops
+    (oracle/, `kind: port`), run with every host thread on a bounded row-slab of the same workload."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import _oracle as orc
+    import immerseflow_b200 as ifx
+    ncx, ncy = args.nx, rows
+    xf = ifx.uniform_faces(ncx, 1.0)
+    yf = ifx.uniform_faces(args.ny, 1.0)[: ncy + 1]
+    g = orc.Grid(xf, yf)
+    u, v, p = orc.initial_condition(g)
+    pr = orc.Predictor(g, u, v, args.dt, args.Re, args.ad_itermax)
+    cores = orc.lib().orc_num_threads()
+    times, k_ad, k_ppe = [], 0, 0
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        k_ad, _ = pr.step()
+        k_ppe, p, _ = orc.ppe_solve(g, p, args.ppe_sweeps)
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    cells = ncx * ncy
+    t = float(np.mean(times))
+    return {"value": cells / t / 1e6, "unit": METRIC, "cores": cores, "kind": "port",
+            "sample": f"{ncx}x{ncy}-cell row slab of the workload, {steps} steps (K_AD={k_ad}, {k_ppe} Poisson sweeps), "
+                      f"OpenMP x{cores}", "ms_per_step": t * 1e3}
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    config = {"workload": f"vortex IC on uniform {args.nx}x{args.ny} cells, reference BCs (u=1,v=0), no immersed body, "
+                          f"dt={args.dt}, Re={args.Re}, AD_itermax={args.ad_itermax}, {args.ppe_sweeps} Poisson sweeps/step",
+              "grid": [args.nx, args.ny], "l2": "working set 17 GB >> 126 MB L2 (no flush needed)"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        steps = max(1, min(args.steps, 3))
+        cb = cpu_reference_arm(args, args.cpu_sample_rows, steps, min(args.warmup, 1))
+        line = {"metric": METRIC, "value": cb["value"], "unit": METRIC, "n_gpus": args.gpus, "steps": steps,
+                "warmup": min(args.warmup, 1), "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference", "config": config,
+                "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": cb["value"], "unit": METRIC, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import immerseflow_b200 as ifx
+
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl")
+    dev = local_rank if world > 1 else 0
+    torch.cuda.set_device(dev)
+
+    ncx, ncy = args.nx, args.ny
+    inp = ifx.make_input(ncx, ncy, args.dt, args.Re, AD_itermax=args.ad_itermax, PPE_itermax=args.ppe_sweeps)
+    xf, yf = ifx.uniform_faces(ncx, 1.0), ifx.uniform_faces(ncy, 1.0)
+    if world > 1:
+        raise SystemExit("multi-GPU slabs: not built yet in this revision")
+    s = ifx.ImmerseFlow(inp, xf, yf, device=dev, sweeps_per_batch=args.ppe_sweeps + 1)
+    s.initializeData()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_step():
+        a = s.ADsolver()
+        b = s.PPESolver()
+        return a, b
+
+    for _ in range(args.warmup):
+        one_step()
+    sampler = ClockSampler(dev)
+    barrier()
+    sampler.start()
+    l0 = s.launch_count
+    t0 = time.perf_counter()
+    ad_ms, ppe_ms, k_ad, k_ppe = [], [], 0, 0
+    for _ in range(args.steps):
+        a, b = one_step()
+        ad_ms.append(a.ms_ad); ppe_ms.append(b.ms_ppe); k_ad, k_ppe = a.ad_iters, b.ppe_sweeps
+    barrier()
+    wall = time.perf_counter() - t0
+    launches = s.launch_count - l0
+    clocks = sampler.stop()
+    # device time of the step = CUDA-event stage timers (both stages run on the solver's stream back to back)
+    dev_ms = float(np.mean(ad_ms) + np.mean(ppe_ms))
+    if world > 1:
+        t = torch.tensor([dev_ms, wall * 1e3 / args.steps], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms, wall_ms = t.tolist()
+    else:
+        wall_ms = wall * 1e3 / args.steps
+    cells = ncx * ncy
+    value = cells / (wall_ms * 1e-3) / 1e6
+
+    # ---- roofline of the dominant kernel (k_ad_jacobi: 25 launches/step vs ~51 Poisson launches of 1/3 the bytes)
+    peak, peak_src = peaks()
+    ad_launch_ms = float(np.mean(ad_ms)) / (k_ad + 1.0 * 48 / 48) if k_ad else None   # source pass ~ one more sweep
+    jac_bytes = 49.0 * cells                     # read u,v,sx,sy + write u',v' (48 B/cell) + 1 B cell type
+    ppe_launch_ms = float(np.mean(ppe_ms)) / (k_ppe + 1)
+    ppe_bytes = 16.0 * cells                     # Laplace variant as the reference ships it: read p, write p'
+    ach_ad = jac_bytes / (ad_launch_ms * 1e-3) / 1e9 if ad_launch_ms else 0.0
+    ach_ppe = ppe_bytes / (ppe_launch_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "k_ad_jacobi", "achieved": ach_ad, "peak": peak, "unit": "GB/s",
+                "frac": ach_ad / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_cell": 49, "ms_per_launch": ad_launch_ms,
+                "poisson": {"kernel": "k_ppe_sweep<laplace>", "achieved": ach_ppe, "frac": ach_ppe / peak,
+                            "algorithmic_bytes_per_cell": 16, "ms_per_launch": ppe_launch_ms,
+                            "sweeps_per_s": 1e3 / ppe_launch_ms}}
+
+    # ---- e2e: same step through the C-ABI with HOST buffers (pinned): H2D of u,v,p, step, D2H of u,v,p
+    e2e = None
+    if not args.no_e2e:
+        n = s.field_size("u")
+        host = {k: torch.empty(n, dtype=torch.float64, pin_memory=True).numpy() for k in ("u", "v", "p")}
+        for k in host:
+            s.get(k, host[k])
+        reps = max(1, min(args.steps, 2))
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            for k in host:
+                s.set(k, host[k])
+            one_step()
+            for k in host:
+                s.get(k, host[k])
+        barrier()
+        te = (time.perf_counter() - t0) / reps
+        e2e = {"value": cells / te / 1e6, "unit": METRIC, "h2d_bytes_per_step": 3 * 8 * n, "d2h_bytes_per_step": 3 * 8 * n,
+               "ms_per_step": te * 1e3}
+
+    line = {"metric": METRIC, "value": value, "unit": METRIC, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": wall_ms, "device_ms_per_step": dev_ms, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+            "iters": {"ad": k_ad, "ppe_sweeps": k_ppe}, "roofline": roofline, "gpu_launches": launches,
+            "clocks": clocks, "e2e": e2e}
+    if rank == 0 and not args.no_cpu_baseline:
+        cb = cpu_reference_arm(args, args.cpu_sample_rows, 1, 1)
+        line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    s.close()
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,695 @@
+// capi.cu — C-ABI entry points (include/immerseflow_c.h) and the host-side solver loops.
+// Host arithmetic in this file is compiled with -ffp-contract=off and uses std::fma explicitly so
+// the 1-D coefficient tables carry the same bits the reference's per-cell kernels produce.
+#include "solver.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+using namespace ifx;
+
+static thread_local std::string g_create_error;
+
+namespace ifx {
+int fail(ifx_solver* s, int code, const std::string& msg) {
+  if (s) s->err = msg; else g_create_error = msg;
+  return code;
+}
+}  // namespace ifx
+
+extern "C" const char* ifx_last_error(const ifx_solver* s) {
+  return s ? s->err.c_str() : g_create_error.c_str();
+}
+
+extern "C" int ifx_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+extern "C" void ifx_default_options(ifx_options* o) {
+  if (!o) return;
+  std::memset(o, 0, sizeof(*o));
+  o->abi_version = IFX_ABI_VERSION;
+  o->device = 0;
+  o->compat = IFX_COMPAT_REFERENCE;
+  o->reduce_mode = IFX_REDUCE_FUSED;
+  // the reference's hard-coded boundary values (ADSolver.cu:200-216)
+  o->bc.u_bc_w = o->bc.u_bc_e = o->bc.u_bc_n = o->bc.u_bc_s = 1.0;
+  o->bc.v_bc_w = o->bc.v_bc_e = o->bc.v_bc_n = o->bc.v_bc_s = 0.0;
+  o->ad_tol = std::pow(10.0, -6.0);    // ADSolver.cu:315
+  o->ppe_tol = std::pow(10.0, -6.0);   // PPESolver.cu:172
+  o->ppe_abs_residual = 0;
+  o->rank = 0; o->nranks = 1;
+  o->j_begin = 0; o->j_end = 0;        // 0,0 = whole grid
+  o->sweeps_per_batch = 64;
+  o->use_graphs = 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// helpers
+// ------------------------------------------------------------------------------------------------
+static int upload_table(ifx_solver* s, const std::vector<double>& h, const double** dst) {
+  double* d = nullptr;
+  IFX_CUDA(s, cudaMalloc(&d, sizeof(double) * h.size()));
+  s->tables.push_back(d);
+  IFX_CUDA(s, cudaMemcpy(d, h.data(), sizeof(double) * h.size(), cudaMemcpyHostToDevice));
+  *dst = d;
+  return IFX_OK;
+}
+
+// Grid metrics and separable stencil coefficients (a2, a3, a11 of SURVEY §8): the reference's
+// per-cell expressions (preSim.cu:294-355, ADSolver.cu:27-39, PPESolver.cu:88-99) evaluated once
+// per column / row instead of once per cell per step.
+static int build_metrics(ifx_solver* s, const double* xf, const double* yf) {
+  const int nx = s->in.nx, ny = s->in.ny;
+  const double dt = s->in.dt, Re = s->in.Re;
+  auto centres = [](int n, const double* f, std::vector<double>& c, std::vector<double>& d) {
+    const int nf = n - 1;
+    c.assign(n, 0.0); d.assign(n, 0.0);
+    for (int i = 1; i < n - 1; i++) c[i] = (f[i - 1] + f[i]) / 2.0;           // preSim.cu:294-301
+    c[0] = -1 * c[1];                                                        // :304-305
+    c[n - 1] = f[nf - 1] + (f[nf - 1] - c[n - 2]);                           // :306-307
+    for (int i = 1; i < n - 1; i++) d[i] = f[i] - f[i - 1];                  // :331-332
+    d[0] = d[1]; d[n - 1] = d[n - 2];                                        // :337-355
+  };
+  centres(nx, xf, s->h_xc, s->h_dx);
+  centres(ny, yf, s->h_yc, s->h_dy);
+
+  const double k = dt / Re;                                                  // ADSolver.cu:34 (div.rn)
+  auto coeffs = [&](int n, const std::vector<double>& d, std::vector<double>& rcp, std::vector<double>& kh,
+                    std::vector<double>& adP, std::vector<double>& adM, std::vector<double>& adS,
+                    std::vector<double>& ppP, std::vector<double>& ppM, std::vector<double>& ppS, bool x_dir) {
+    rcp.assign(n, 0.0); kh.assign(n, 0.0);
+    adP.assign(n, 1.0); adM.assign(n, 1.0); adS.assign(n, 1.0);
+    ppP.assign(n, 1.0); ppM.assign(n, 1.0); ppS.assign(n, 1.0);
+    for (int i = 0; i < n - 1; i++) rcp[i] = 1.0 / (d[i] + d[i + 1]);         // ADSolver.cu:66 (rcp.rn)
+    for (int i = 0; i < n; i++) kh[i] = (dt / d[i]) * 0.5;                    // ADSolver.cu:66
+    for (int i = 1; i < n - 1; i++) {
+      const double a_p = 2.0 / (d[i] * (d[i] + d[i + 1]));
+      const double a_m = 2.0 / (d[i] * (d[i] + d[i - 1]));
+      adP[i] = k * a_p;                                                      // ADSolver.cu:37,39
+      adM[i] = k * a_m;                                                      // ADSolver.cu:36,38
+      // x: first half of cP, fma(k, ax_p+ax_m, 1.0); y: the bare sum, folded in per cell
+      adS[i] = x_dir ? std::fma(k, a_p + a_m, 1.0) : (a_p + a_m);
+      ppP[i] = a_p; ppM[i] = a_m; ppS[i] = a_p + a_m;                        // PPESolver.cu:93-99
+    }
+  };
+  std::vector<double> rcpx, kxh, adE, adW, adPx, ppE, ppW, ppSx;
+  std::vector<double> rcpy, kyh, adN, adS, adSy, ppN, ppS, ppSy;
+  coeffs(nx, s->h_dx, rcpx, kxh, adE, adW, adPx, ppE, ppW, ppSx, true);
+  coeffs(ny, s->h_dy, rcpy, kyh, adN, adS, adSy, ppN, ppS, ppSy, false);
+
+  Metrics& M = s->M;
+  int rc;
+#define UP(vec, field) if ((rc = upload_table(s, vec, &M.field)) != IFX_OK) return rc;
+  UP(s->h_dx, dx) UP(s->h_dy, dy) UP(s->h_xc, xc) UP(s->h_yc, yc)
+  UP(rcpx, rcpx) UP(rcpy, rcpy) UP(kxh, kxh) UP(kyh, kyh)
+  UP(adE, ad_cE) UP(adW, ad_cW) UP(adPx, ad_px) UP(adN, ad_cN) UP(adS, ad_cS) UP(adSy, ad_sy)
+  UP(ppE, pp_cE) UP(ppW, pp_cW) UP(ppSx, pp_sx) UP(ppN, pp_cN) UP(ppS, pp_cS) UP(ppSy, pp_sy)
+#undef UP
+  M.k = k;
+  M.dt = dt;
+  return IFX_OK;
+}
+
+static int rows_per_cta_for(const ifx_solver* s) {
+  // enough CTAs for >= ~6 per SM when the grid allows it, tall tiles (less halo re-read) otherwise
+  const int nxi = s->L.nx - 2, nyi = s->L.je - s->L.jb;
+  const int gx = (nxi + TILE_COLS - 1) / TILE_COLS;
+  int ry = 64;
+  while (ry > 4 && (long long)gx * ((nyi + ry - 1) / ry) < 148LL * 6) ry >>= 1;
+  return ry;
+}
+
+static dim3 tile_grid(const ifx_solver* s, int ry) {
+  const int nxi = s->L.nx - 2, nyi = s->L.je - s->L.jb;
+  return dim3((nxi + TILE_COLS - 1) / TILE_COLS, (nyi + ry - 1) / ry, 1);
+}
+
+static int ensure_partials(ifx_solver* s, size_t nblocks) {
+  if (nblocks <= s->partials_cap) return IFX_OK;
+  if (s->partials) cudaFree(s->partials);
+  s->partials = nullptr;
+  IFX_CUDA(s, cudaMalloc(&s->partials, sizeof(double) * 2 * nblocks));
+  s->partials_cap = nblocks;
+  return IFX_OK;
+}
+
+static int ensure_exact_buffers(ifx_solver* s) {
+  if (s->res_a) return IFX_OK;
+  if (s->opt.nranks != 1)
+    return fail(s, IFX_ERR_INVALID, "reference-order reduction is single-GPU only");
+  const size_t N = (size_t)s->L.nx * s->L.ny;
+  IFX_CUDA(s, cudaMalloc(&s->res_a, sizeof(double) * N));
+  IFX_CUDA(s, cudaMalloc(&s->res_b, sizeof(double) * N));
+  IFX_CUDA(s, cudaMemsetAsync(s->res_a, 0, sizeof(double) * N, s->stream));
+  IFX_CUDA(s, cudaMemsetAsync(s->res_b, 0, sizeof(double) * N, s->stream));
+  IFX_CUDA(s, cudaMalloc(&s->red_partial, sizeof(double) * ((N + 255) / 256)));
+  return IFX_OK;
+}
+
+// ImmerseFlow::Reduction (preSim.cu:376-445) on a device array of n doubles -> *out (device)
+static int reduce_reference_order(ifx_solver* s, const double* d_in, size_t n, double* d_out) {
+  s->launches += 2;
+  IFX_CUDA(s, launch_reduce6(d_in, n, s->red_partial, d_out, s->stream));
+  return IFX_OK;
+}
+
+static int fetch_ctl(ifx_solver* s) {
+  IFX_CUDA(s, cudaMemcpyAsync(s->h_ctl, s->ctl, sizeof(LoopCtl), cudaMemcpyDeviceToHost, s->stream));
+  IFX_CUDA(s, cudaStreamSynchronize(s->stream));
+  return IFX_OK;
+}
+
+static void fill_bc(const ifx_solver* s, double* two_u, double* two_v) {
+  const ifx_bc& b = s->opt.bc;
+  two_u[0] = b.u_bc_w * 2.0; two_u[1] = b.u_bc_e * 2.0; two_u[2] = b.u_bc_s * 2.0; two_u[3] = b.u_bc_n * 2.0;
+  two_v[0] = b.v_bc_w * 2.0; two_v[1] = b.v_bc_e * 2.0; two_v[2] = b.v_bc_s * 2.0; two_v[3] = b.v_bc_n * 2.0;
+}
+
+// Half-width (relative to the sum of magnitudes) of the band inside which the fused summation order
+// and the reference's could disagree about `sum > tol`: gamma_d with d = the deepest chain of
+// additions either order applies to one term, times a safety factor of 2.
+static double rounding_band(const ifx_solver* s, size_t nblocks, int rows_per_cta) {
+  const double N = (double)s->L.nx * s->L.ny;
+  const double d_ref = 10.0 + std::ceil(N / 256.0 / 512.0) + 1.0 + 8.0 + 2.0;
+  const double d_fused = 2.0 * rows_per_cta + 5.0 + AD_WARPS + std::ceil((double)nblocks / AD_THREADS) + 5.0 + AD_WARPS + 2.0;
+  return 2.0 * (d_ref + d_fused) * 1.1102230246251565e-16;
+}
+
+// ------------------------------------------------------------------------------------------------
+// lifetime
+// ------------------------------------------------------------------------------------------------
+extern "C" int ifx_create(const ifx_input* in, const double* xf, const double* yf,
+                          const ifx_options* opt_in, ifx_solver** out) {
+  if (!in || !xf || !yf || !out) return fail(nullptr, IFX_ERR_INVALID, "null argument");
+  *out = nullptr;
+  ifx_options opt;
+  if (opt_in) opt = *opt_in; else ifx_default_options(&opt);
+  if (opt.abi_version != IFX_ABI_VERSION) return fail(nullptr, IFX_ERR_INVALID, "ABI version mismatch");
+  if (in->nx < 4 || in->ny < 4) return fail(nullptr, IFX_ERR_INVALID, "grid too small");
+  if ((long long)in->nx * in->ny >= (1LL << 31)) return fail(nullptr, IFX_ERR_INVALID, "nx*ny must fit 32-bit ids");
+  if (opt.j_begin == 0 && opt.j_end == 0) { opt.j_begin = 1; opt.j_end = in->ny - 1; }
+  if (opt.j_begin < 1 || opt.j_end > in->ny - 1 || opt.j_begin >= opt.j_end)
+    return fail(nullptr, IFX_ERR_INVALID, "bad slab rows");
+  if (opt.sweeps_per_batch < 1) opt.sweeps_per_batch = 64;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(nullptr, IFX_ERR_CUDA, "no CUDA device: the B200 kernels are the only implementation (no CPU fallback)");
+  }
+  if (opt.device < 0 || opt.device >= ndev) return fail(nullptr, IFX_ERR_INVALID, "bad device ordinal");
+
+  ifx_solver* s = new (std::nothrow) ifx_solver();
+  if (!s) return fail(nullptr, IFX_ERR_NOMEM, "host allocation failed");
+  s->in = *in;
+  s->opt = opt;
+  s->device = opt.device;
+  auto bail = [&](int code) { g_create_error = s->err; ifx_destroy(s); return code; };
+
+  cudaError_t e = cudaSetDevice(s->device);
+  if (e != cudaSuccess) { s->err = cudaGetErrorString(e); return bail(IFX_ERR_CUDA); }
+  e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) { s->err = cudaGetErrorString(e); return bail(IFX_ERR_CUDA); }
+  s->own_stream = true;
+
+  Layout& L = s->L;
+  L.nx = in->nx; L.ny = in->ny;
+  L.pitch = ((IFX_PADL + in->nx + 1) + 15) / 16 * 16;      // +1: a double2 may straddle the last column
+  L.jb = opt.j_begin; L.je = opt.j_end;
+  L.j0 = opt.j_begin - 1;
+  L.nyl = (opt.j_end - opt.j_begin) + 2;
+  s->field_elems = (size_t)L.pitch * L.nyl + 64;
+
+  int rc = build_metrics(s, xf, yf);
+  if (rc != IFX_OK) return bail(rc);
+
+  auto alloc_field = [&](double** p) -> int {
+    IFX_CUDA(s, cudaMalloc(p, sizeof(double) * s->field_elems));
+    IFX_CUDA(s, cudaMemsetAsync(*p, 0, sizeof(double) * s->field_elems, s->stream));
+    return IFX_OK;
+  };
+  double** fields[] = {&s->u[0], &s->u[1], &s->v[0], &s->v[1], &s->p[0], &s->p[1], &s->sx, &s->sy};
+  for (double** f : fields)
+    if ((rc = alloc_field(f)) != IFX_OK) return bail(rc);
+  if (opt.compat == IFX_COMPAT_FULL || in->nx > in->ny) {
+    if ((rc = alloc_field(&s->uf)) != IFX_OK) return bail(rc);
+    if ((rc = alloc_field(&s->vf)) != IFX_OK) return bail(rc);
+  }
+  if (opt.compat == IFX_COMPAT_FULL)
+    if ((rc = alloc_field(&s->rhs)) != IFX_OK) return bail(rc);
+  if (cudaMalloc(&s->celltype, s->field_elems) != cudaSuccess) { s->err = "cudaMalloc celltype"; return bail(IFX_ERR_CUDA); }
+  launch_fill_u8(s->celltype, s->field_elems, IFX_FLUID, s->stream);
+  s->launches++;
+  if (cudaMalloc(&s->ctl, sizeof(LoopCtl)) != cudaSuccess || cudaMallocHost(&s->h_ctl, sizeof(LoopCtl)) != cudaSuccess ||
+      cudaMalloc(&s->red_out, sizeof(double) * 4) != cudaSuccess) {
+    s->err = "control block allocation failed";
+    return bail(IFX_ERR_CUDA);
+  }
+  cudaMemsetAsync(s->ctl, 0, sizeof(LoopCtl), s->stream);
+  for (auto& ev : s->ev) cudaEventCreate(&ev);
+  e = cudaStreamSynchronize(s->stream);
+  if (e != cudaSuccess) { s->err = cudaGetErrorString(e); return bail(IFX_ERR_CUDA); }
+  *out = s;
+  return IFX_OK;
+}
+
+extern "C" int ifx_destroy(ifx_solver* s) {
+  if (!s) return IFX_OK;
+  cudaSetDevice(s->device);
+  if (s->stream) cudaStreamSynchronize(s->stream);
+  double* fields[] = {s->u[0], s->u[1], s->v[0], s->v[1], s->p[0], s->p[1], s->sx, s->sy, s->rhs, s->uf, s->vf,
+                      s->partials, s->res_a, s->res_b, s->red_partial, s->red_out, s->d_xm, s->d_ym, s->d_ub, s->d_vb,
+                      s->gc.w_dir, s->gc.w_neu, s->gc.bi, s->gc.ip};
+  for (double* f : fields) if (f) cudaFree(f);
+  int* ifields[] = {s->d_body_off, s->gc.cell, s->gc.ref_id, s->gc.stencil, s->gc.stencil_ref, s->gc.body,
+                    s->d_counters, s->d_rowcount};
+  for (int* f : ifields) if (f) cudaFree(f);
+  for (double* t : s->tables) cudaFree(t);
+  if (s->celltype) cudaFree(s->celltype);
+  if (s->ctl) cudaFree(s->ctl);
+  if (s->h_ctl) cudaFreeHost(s->h_ctl);
+  for (auto& ev : s->ev) if (ev) cudaEventDestroy(ev);
+  if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
+  delete s;
+  return IFX_OK;
+}
+
+extern "C" int ifx_set_stream(ifx_solver* s, void* stream) {
+  if (!s) return IFX_ERR_INVALID;
+  cudaSetDevice(s->device);
+  if (s->stream) cudaStreamSynchronize(s->stream);
+  if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
+  s->stream = (cudaStream_t)stream;
+  s->own_stream = false;
+  return IFX_OK;
+}
+
+extern "C" int ifx_synchronize(ifx_solver* s) {
+  if (!s) return IFX_ERR_INVALID;
+  IFX_CUDA(s, cudaSetDevice(s->device));
+  IFX_CUDA(s, cudaStreamSynchronize(s->stream));
+  return IFX_OK;
+}
+
+extern "C" long long ifx_launch_count(const ifx_solver* s) { return s ? s->launches : 0; }
+
+// initializeData (preSim.cu:201-217): vortex IC, iBlank.  In IFX_COMPAT_REFERENCE iBlank == 1
+// (preSim.cu:133); with bodies set (ifx_set_bodies) the classification runs in ifx_iblank_update.
+extern "C" int ifx_initialize(ifx_solver* s) {
+  if (!s) return IFX_ERR_INVALID;
+  IFX_CUDA(s, cudaSetDevice(s->device));
+  const Layout& L = s->L;
+  for (int b = 0; b < 2; b++) {   // both ping-pong partners start from the same field
+    s->launches++;
+    IFX_CUDA(s, launch_init_vortex(L, s->M.xc, s->M.yc, s->u[b], s->v[b], s->p[b], s->stream));
+  }
+  s->cur_uv = 0; s->cur_p = 0;
+  s->launches++;
+  IFX_CUDA(s, launch_fill_u8(s->celltype, s->field_elems, IFX_FLUID, s->stream));
+  if (s->uf) {   // initializeKernel zeroes the face arrays (preSim.cu:79-96)
+    IFX_CUDA(s, cudaMemsetAsync(s->uf, 0, sizeof(double) * s->field_elems, s->stream));
+    IFX_CUDA(s, cudaMemsetAsync(s->vf, 0, sizeof(double) * s->field_elems, s->stream));
+  }
+  s->faces_valid = false;
+  s->initialized = true;
+  IFX_CUDA(s, cudaStreamSynchronize(s->stream));
+  return IFX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// state access
+// ------------------------------------------------------------------------------------------------
+struct FieldView { double* dev; int i0, width, jl0, rows; bool is_u8; int raw; const double* table; };
+
+static int field_view(ifx_solver* s, ifx_field f, FieldView* v) {
+  const Layout& L = s->L;
+  *v = FieldView{nullptr, 0, L.nx, 0, L.nyl, false, 0, nullptr};
+  switch (f) {
+    case IFX_FIELD_U: v->dev = s->u[s->cur_uv]; break;
+    case IFX_FIELD_V: v->dev = s->v[s->cur_uv]; break;
+    case IFX_FIELD_P: v->dev = s->p[s->cur_p]; break;
+    case IFX_FIELD_SX: v->dev = s->sx; break;
+    case IFX_FIELD_SY: v->dev = s->sy; break;
+    case IFX_FIELD_PPE_RHS: v->dev = s->rhs; break;
+    case IFX_FIELD_IBLANK: v->is_u8 = true; v->raw = 0; break;
+    case IFX_FIELD_CELLTYPE: v->is_u8 = true; v->raw = 1; break;
+    // UF(i,j) = face east of cell (i,j): i = 0..nx-2 on interior rows  (Data.u.velf, ADSolver.cu:167-177)
+    case IFX_FIELD_UF: v->dev = s->uf; v->i0 = 0; v->width = L.nx - 1; v->jl0 = 1; v->rows = L.nyl - 2; break;
+    // VF(i,j) = face north of cell (i,j): i = 1..nx-2, j = 0..ny-2     (Data.v.velf, ADSolver.cu:179-186)
+    case IFX_FIELD_VF: v->dev = s->vf; v->i0 = 1; v->width = L.nx - 2; v->jl0 = 0; v->rows = L.nyl - 1; break;
+    case IFX_FIELD_XC: v->table = s->h_xc.data(); v->width = L.nx; v->rows = 1; break;
+    case IFX_FIELD_YC: v->table = s->h_yc.data(); v->width = L.ny; v->rows = 1; break;
+    default: return fail(s, IFX_ERR_INVALID, "unknown field");
+  }
+  if (!v->table && !v->is_u8 && !v->dev) return fail(s, IFX_ERR_STATE, "field not allocated in this mode");
+  return IFX_OK;
+}
+
+extern "C" size_t ifx_field_size(const ifx_solver* s, ifx_field f) {
+  if (!s) return 0;
+  FieldView v;
+  if (field_view(const_cast<ifx_solver*>(s), f, &v) != IFX_OK) return 0;
+  return (size_t)v.width * v.rows;
+}
+
+extern "C" int ifx_set_field(ifx_solver* s, ifx_field f, const double* host, size_t n) {
+  if (!s || !host) return IFX_ERR_INVALID;
+  IFX_CUDA(s, cudaSetDevice(s->device));
+  FieldView v;
+  int rc = field_view(s, f, &v);
+  if (rc != IFX_OK) return rc;
+  if (v.table || v.is_u8) return fail(s, IFX_ERR_INVALID, "field is read-only");
+  if (n != (size_t)v.width * v.rows) return fail(s, IFX_ERR_INVALID, "size mismatch");
+  const Layout& L = s->L;
+  IFX_CUDA(s, cudaMemcpy2DAsync(v.dev + lidx(L, v.i0, v.jl0), sizeof(double) * L.pitch, host,
+                                sizeof(double) * v.width, sizeof(double) * v.width, v.rows,
+                                cudaMemcpyHostToDevice, s->stream));
+  if (f == IFX_FIELD_U || f == IFX_FIELD_V || f == IFX_FIELD_P) {
+    // keep the ping-pong partner's ghost ring consistent (a freshly set state has no history)
+    double* other = (f == IFX_FIELD_U) ? s->u[s->cur_uv ^ 1] : (f == IFX_FIELD_V) ? s->v[s->cur_uv ^ 1] : s->p[s->cur_p ^ 1];
+    s->launches++;
+    IFX_CUDA(s, launch_copy_ring(L, v.dev, other, nullptr, nullptr, s->stream));
+    if (f != IFX_FIELD_P) s->faces_valid = false;
+  }
+  if (f == IFX_FIELD_UF || f == IFX_FIELD_VF) s->faces_valid = true;
+  IFX_CUDA(s, cudaStreamSynchronize(s->stream));
+  return IFX_OK;
+}
+
+extern "C" int ifx_get_field(ifx_solver* s, ifx_field f, double* host, size_t n) {
+  if (!s || !host) return IFX_ERR_INVALID;
+  IFX_CUDA(s, cudaSetDevice(s->device));
+  FieldView v;
+  int rc = field_view(s, f, &v);
+  if (rc != IFX_OK) return rc;
+  if (n != (size_t)v.width * v.rows) return fail(s, IFX_ERR_INVALID, "size mismatch");
+  const Layout& L = s->L;
+  if (v.table) { std::memcpy(host, v.table, sizeof(double) * n); return IFX_OK; }
+  if (v.is_u8) {
+    double* tmp = nullptr;
+    IFX_CUDA(s, cudaMalloc(&tmp, sizeof(double) * n));
+    s->launches++;
+    cudaError_t e = launch_pack_u8(L, s->celltype, tmp, v.raw, s->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(host, tmp, sizeof(double) * n, cudaMemcpyDeviceToHost, s->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+    cudaFree(tmp);
+    IFX_CUDA(s, e);
+    return IFX_OK;
+  }
+  IFX_CUDA(s, cudaMemcpy2DAsync(host, sizeof(double) * v.width, v.dev + lidx(L, v.i0, v.jl0), sizeof(double) * L.pitch,
+                                sizeof(double) * v.width, v.rows, cudaMemcpyDeviceToHost, s->stream));
+  IFX_CUDA(s, cudaStreamSynchronize(s->stream));
+  return IFX_OK;
+}
+
+// saveDataToFile (postSim.cu:10-39): D2H then the Tecplot writer.
+extern "C" int ifx_save_field(ifx_solver* s, ifx_field f, const char* filename) {
+  if (!s || !filename) return IFX_ERR_INVALID;
+  if (s->opt.nranks != 1) return fail(s, IFX_ERR_INVALID, "ifx_save_field: gather the slabs first");
+  const size_t n = ifx_field_size(s, f);
+  if (n != (size_t)s->L.nx * s->L.ny) return fail(s, IFX_ERR_INVALID, "only cell-centred fields can be saved");
+  std::vector<double> h(n);
+  int rc = ifx_get_field(s, f, h.data(), n);
+  if (rc != IFX_OK) return rc;
+  rc = ifx_write_results_to_file(s->h_xc.data(), s->h_yc.data(), h.data(), s->L.nx, s->L.ny, filename);
+  if (rc != IFX_OK) return fail(s, rc, std::string("cannot write ") + filename);
+  return IFX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Reduction (preSim.cu:376-445) on host data
+// ------------------------------------------------------------------------------------------------
+extern "C" int ifx_reduce_sum(ifx_solver* s, const double* host, size_t n, double* out) {
+  if (!s || !host || !out || n == 0 || n >= (1ull << 31)) return IFX_ERR_INVALID;
+  IFX_CUDA(s, cudaSetDevice(s->device));
+  double *d_in = nullptr, *d_part = nullptr;
+  IFX_CUDA(s, cudaMalloc(&d_in, sizeof(double) * n));
+  IFX_CUDA(s, cudaMalloc(&d_part, sizeof(double) * ((n + 255) / 256)));
+  cudaError_t e = cudaMemcpyAsync(d_in, host, sizeof(double) * n, cudaMemcpyHostToDevice, s->stream);
+  if (e == cudaSuccess) e = launch_reduce6(d_in, n, d_part, s->red_out, s->stream);
+  s->launches += 2;
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out, s->red_out, sizeof(double), cudaMemcpyDeviceToHost, s->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+  cudaFree(d_in); cudaFree(d_part);
+  IFX_CUDA(s, e);
+  return IFX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// predictor — ImmerseFlow::ADsolver(), ADSolver.cu:268-395
+// ------------------------------------------------------------------------------------------------
+static int launch_ad_jacobi(ifx_solver* s, AdJacobiArgs& a, dim3 grid, bool write_res) {
+  s->launches++;
+  IFX_CUDA(s, ifx::launch_ad_jacobi(a, grid, s->stream, write_res, s->has_gc));
+  return IFX_OK;
+}
+
+// reference-order evaluation of the two residual arrays + stop decision (ADSolver.cu:360-366, :315)
+static int exact_decide(ifx_solver* s, const ReduceCfg& rc, bool two_arrays) {
+  const size_t N = (size_t)s->L.nx * s->L.ny;
+  int r = reduce_reference_order(s, s->res_a, N, s->red_out);
+  if (r != IFX_OK) return r;
+  if (two_arrays) {
+    if ((r = reduce_reference_order(s, s->res_b, N, s->red_out + 1)) != IFX_OK) return r;
+  } else {
+    IFX_CUDA(s, cudaMemsetAsync(s->red_out + 1, 0, sizeof(double), s->stream));
+  }
+  s->launches++;
+  IFX_CUDA(s, launch_decide_exact(s->ctl, s->red_out, rc, s->stream));
+  return IFX_OK;
+}
+
+extern "C" int ifx_ad_solve(ifx_solver* s, ifx_step_stats* st) {
+  if (!s) return IFX_ERR_INVALID;
+  IFX_CUDA(s, cudaSetDevice(s->device));
+  const Layout& L = s->L;
+  const bool exact = s->opt.reduce_mode == IFX_REDUCE_REFERENCE;
+  const bool full = s->opt.compat == IFX_COMPAT_FULL;
+  const int itermax = s->in.AD_itermax;
+  const int ry = rows_per_cta_for(s);
+  const dim3 grid = tile_grid(s, ry);
+  const size_t nblocks = (size_t)grid.x * grid.y;
+  int rc = ensure_partials(s, nblocks);
+  if (rc != IFX_OK) return rc;
+  if (exact && (rc = ensure_exact_buffers(s)) != IFX_OK) return rc;
+
+  IFX_CUDA(s, cudaEventRecord(s->ev[0], s->stream));
+  const int base = s->cur_uv;
+
+  // ---- velf + BC + ADSource (ADSolver.cu:298-311) in one pass
+  AdSourceArgs sa{};
+  sa.L = L; sa.M = s->M;
+  sa.u = s->u[base]; sa.v = s->v[base];
+  sa.uf = s->uf; sa.vf = s->vf;
+  sa.sx = s->sx; sa.sy = s->sy;
+  fill_bc(s, sa.two_bc_u, sa.two_bc_v);
+  sa.rows_per_cta = ry;
+  if (full) {
+    if (!s->faces_valid) return fail(s, IFX_ERR_STATE, "face velocities not initialised (call ifx_step / ifx_iblank_update)");
+    IFX_CUDA(s, launch_ad_source(sa, grid, s->stream, SRC_FACES));
+  } else if (L.nx <= L.ny) {
+    IFX_CUDA(s, launch_ad_source(sa, grid, s->stream, SRC_REF_VF_ZERO));     // vf == 0 (App. A Q2)
+  } else {
+    return fail(s, IFX_ERR_INVALID, "IFX_COMPAT_REFERENCE with nx > ny: the reference overruns its vf allocation "
+                                    "(preSim.cu:153, ADSolver.cu:179-186); use IFX_COMPAT_FULL");
+  }
+  s->launches++;
+
+  IFX_CUDA(s, cudaMemsetAsync(s->ctl, 0, sizeof(LoopCtl), s->stream));
+  if (itermax <= 0) {   // while-condition false on entry: zero iterations (ADSolver.cu:315)
+    if (st) { st->ad_iters = 0; st->ad_ures = 1.0; st->ad_vres = 1.0; }
+    return IFX_OK;
+  }
+
+  AdJacobiArgs ja{};
+  ja.L = L; ja.M = s->M;
+  ja.sx = s->sx; ja.sy = s->sy; ja.celltype = s->celltype;
+  ja.res_u = s->res_a; ja.res_v = s->res_b;
+  ja.partials = s->partials; ja.ctl = s->ctl;
+  fill_bc(s, ja.two_bc_u, ja.two_bc_v);
+  ja.rows_per_cta = ry;
+  ja.rc.itermax = itermax; ja.rc.tol = s->opt.ad_tol; ja.rc.use_second = 1; ja.rc.test_abs = 0;
+  ja.rc.decide = exact ? 0 : 1;
+  ja.rc.certify = exact ? 0 : 1;
+  ja.rc.band = rounding_band(s, nblocks, ry);
+
+  auto set_iter = [&](int m) {
+    const int src = (base + m - 1) & 1;
+    ja.uC = s->u[src]; ja.vC = s->v[src];
+    ja.uT = s->u[src ^ 1]; ja.vT = s->v[src ^ 1];
+    ja.rc.eval_iter = m;
+  };
+
+  int m = 0, fallbacks = 0;
+  int batch = std::min(itermax, std::max(1, s->last_ad_iters + 1));
+  for (;;) {
+    const int todo = std::min(batch, itermax - m);
+    for (int b = 0; b < todo; b++) {
+      set_iter(++m);
+      ja.force = 0;
+      if ((rc = launch_ad_jacobi(s, ja, grid, exact)) != IFX_OK) return rc;
+      if (exact && (rc = exact_decide(s, ja.rc, true)) != IFX_OK) return rc;
+    }
+    if ((rc = fetch_ctl(s)) != IFX_OK) return rc;
+    if (s->h_ctl->done && s->h_ctl->ambiguous) {
+      // the fused sum of iteration h_ctl->iter is within rounding of the tolerance: re-evaluate that
+      // iteration's residual in the reference's summation order (iterate and predecessor are intact)
+      fallbacks++;
+      if ((rc = ensure_exact_buffers(s)) != IFX_OK) return rc;
+      ja.res_u = s->res_a; ja.res_v = s->res_b;
+      m = s->h_ctl->iter;
+      set_iter(m);
+      ja.force = 1; ja.rc.decide = 0;
+      if ((rc = launch_ad_jacobi(s, ja, grid, true)) != IFX_OK) return rc;
+      if ((rc = exact_decide(s, ja.rc, true)) != IFX_OK) return rc;
+      ja.rc.decide = 1;
+      if ((rc = fetch_ctl(s)) != IFX_OK) return rc;
+    }
+    if (s->h_ctl->done) break;
+    if (m >= itermax) return fail(s, IFX_ERR_STATE, "predictor loop ran past AD_itermax without a decision");
+    batch = 2;
+  }
+  const int K = s->h_ctl->iter;
+  s->cur_uv = (base + K) & 1;
+  s->last_ad_iters = K;
+  if (K == 1) {   // final buffer's ghost ring was never written this step: give it BC(start field)
+    s->launches++;
+    IFX_CUDA(s, launch_copy_ring(L, s->u[base], s->u[s->cur_uv], s->v[base], s->v[s->cur_uv], s->stream));
+  }
+  IFX_CUDA(s, cudaEventRecord(s->ev[1], s->stream));
+  IFX_CUDA(s, cudaEventSynchronize(s->ev[1]));
+  if (st) {
+    st->ad_iters = K;
+    st->ad_ures = s->h_ctl->res0;
+    st->ad_vres = s->h_ctl->res1;
+    st->exact_fallbacks += fallbacks;
+    cudaEventElapsedTime(&st->ms_ad, s->ev[0], s->ev[1]);
+  }
+  return IFX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Poisson — ImmerseFlow::PPESolver(), PPESolver.cu:137-205
+// ------------------------------------------------------------------------------------------------
+static int launch_ppe_sweep(ifx_solver* s, PpeSweepArgs& a, dim3 grid, bool laplace_ref, bool write_res) {
+  s->launches++;
+  IFX_CUDA(s, ifx::launch_ppe_sweep(a, grid, s->stream, laplace_ref, write_res, s->has_gc));
+  return IFX_OK;
+}
+
+extern "C" int ifx_ppe_solve(ifx_solver* s, ifx_step_stats* st) {
+  if (!s) return IFX_ERR_INVALID;
+  IFX_CUDA(s, cudaSetDevice(s->device));
+  const Layout& L = s->L;
+  const bool exact = s->opt.reduce_mode == IFX_REDUCE_REFERENCE;
+  const bool laplace_ref = s->opt.compat == IFX_COMPAT_REFERENCE;
+  const int itermax = s->in.PPE_itermax;
+  const int ry = rows_per_cta_for(s);
+  const dim3 grid = tile_grid(s, ry);
+  const size_t nblocks = (size_t)grid.x * grid.y;
+  int rc = ensure_partials(s, nblocks);
+  if (rc != IFX_OK) return rc;
+  if (exact && (rc = ensure_exact_buffers(s)) != IFX_OK) return rc;
+
+  IFX_CUDA(s, cudaEventRecord(s->ev[2], s->stream));
+  const int base = s->cur_p;
+  if (laplace_ref) {
+    // set_pressure_BC (PPESolver.cu:164); the ring is then carried through every sweep (:21)
+    s->launches += 2;
+    IFX_CUDA(s, launch_set_pressure_bc_ref(L, s->p[base], nullptr, s->stream));
+    IFX_CUDA(s, launch_copy_ring(L, s->p[base], s->p[base ^ 1], nullptr, nullptr, s->stream));
+  }
+  IFX_CUDA(s, cudaMemsetAsync(s->ctl, 0, sizeof(LoopCtl), s->stream));
+  int K = 0, fallbacks = 0;
+  if (itermax > 0) {
+    PpeSweepArgs pa{};
+    pa.L = L; pa.M = s->M;
+    pa.rhs = s->rhs; pa.celltype = s->celltype;
+    pa.res = s->res_a; pa.partials = s->partials; pa.ctl = s->ctl;
+    pa.rows_per_cta = ry;
+    pa.rc.itermax = itermax; pa.rc.tol = s->opt.ppe_tol; pa.rc.use_second = 0;
+    pa.rc.test_abs = s->opt.ppe_abs_residual ? 1 : 0;
+    pa.rc.decide = exact ? 0 : 1;
+    pa.rc.certify = exact ? 0 : 1;
+    pa.rc.band = rounding_band(s, nblocks, ry);
+    auto set_sweep = [&](int m) {     // sweep m: iterate m-1 -> iterate m, evaluates residual(iterate m-1)
+      const int src = (base + m - 1) & 1;
+      pa.pC = s->p[src]; pa.pT = s->p[src ^ 1];
+      pa.rc.eval_iter = m - 1;
+    };
+    int m = 0;
+    for (;;) {
+      const int todo = std::min(s->opt.sweeps_per_batch, itermax + 1 - m);
+      for (int b = 0; b < todo; b++) {
+        set_sweep(++m);
+        pa.force = 0;
+        if ((rc = launch_ppe_sweep(s, pa, grid, laplace_ref, exact)) != IFX_OK) return rc;
+        if (exact && m > 1 && (rc = exact_decide(s, pa.rc, false)) != IFX_OK) return rc;
+      }
+      if ((rc = fetch_ctl(s)) != IFX_OK) return rc;
+      if (s->h_ctl->done && s->h_ctl->ambiguous) {
+        fallbacks++;
+        if ((rc = ensure_exact_buffers(s)) != IFX_OK) return rc;
+        pa.res = s->res_a;
+        m = s->h_ctl->iter + 1;          // the sweep that evaluated the ambiguous residual
+        set_sweep(m);
+        pa.force = 1; pa.rc.decide = 0;
+        if ((rc = launch_ppe_sweep(s, pa, grid, laplace_ref, true)) != IFX_OK) return rc;
+        if ((rc = exact_decide(s, pa.rc, false)) != IFX_OK) return rc;
+        pa.rc.decide = 1;
+        if ((rc = fetch_ctl(s)) != IFX_OK) return rc;
+      }
+      if (s->h_ctl->done) break;
+      if (m >= itermax + 1) return fail(s, IFX_ERR_STATE, "Poisson loop ran past PPE_itermax without a decision");
+    }
+    K = s->h_ctl->iter;
+    s->cur_p = (base + K) & 1;
+  }
+  if (laplace_ref) {   // PPESolver.cu:195
+    s->launches++;
+    IFX_CUDA(s, launch_set_pressure_bc_ref(L, s->p[s->cur_p], nullptr, s->stream));
+  }
+  IFX_CUDA(s, cudaEventRecord(s->ev[3], s->stream));
+  IFX_CUDA(s, cudaEventSynchronize(s->ev[3]));
+  if (st) {
+    st->ppe_sweeps = K;
+    st->ppe_residual = (itermax > 0) ? (s->opt.ppe_abs_residual ? s->h_ctl->res1 : s->h_ctl->res0) : 1.0;
+    st->exact_fallbacks += fallbacks;
+    cudaEventElapsedTime(&st->ms_ppe, s->ev[2], s->ev[3]);
+  }
+  return IFX_OK;
+}
+
+extern "C" int ifx_correct(ifx_solver* s, ifx_step_stats* st) {
+  (void)st;
+  if (!s) return IFX_ERR_INVALID;
+  return fail(s, IFX_ERR_INVALID, "ifx_correct requires IFX_COMPAT_FULL (the reference has no projection, AD_PPE_Correction.cu:1-12)");
+}
+
+// one iteration of main()'s time loop (main.cu:93-96)
+extern "C" int ifx_step(ifx_solver* s, ifx_step_stats* st) {
+  if (!s) return IFX_ERR_INVALID;
+  if (st) std::memset(st, 0, sizeof(*st));
+  if (s->opt.compat == IFX_COMPAT_REFERENCE) {
+    int rc = ifx_ad_solve(s, st);
+    if (rc == IFX_OK && st) st->ms_total = st->ms_ad;
+    return rc;
+  }
+  return fail(s, IFX_ERR_INVALID, "IFX_COMPAT_FULL step not built yet");
+}
+
+extern "C" int ifx_set_bodies(ifx_solver* s, int, const int*, const double*, const double*, const double*, const double*) {
+  return fail(s, IFX_ERR_INVALID, "immersed bodies not built yet");
+}
+extern "C" int ifx_iblank_update(ifx_solver* s, ifx_step_stats*) { return fail(s, IFX_ERR_INVALID, "immersed bodies not built yet"); }
+extern "C" int ifx_ghost_cell_count(const ifx_solver* s) { return s ? s->gc.count : 0; }
+extern "C" int ifx_get_ghost_cells(ifx_solver* s, int*, int*, double*, double*, double*, int) {
+  return fail(s, IFX_ERR_INVALID, "immersed bodies not built yet");
+}
+extern "C" int ifx_ipc_export(ifx_solver* s, unsigned char*) { return fail(s, IFX_ERR_INVALID, "multi-GPU not built yet"); }
+extern "C" int ifx_ipc_connect(ifx_solver* s, const unsigned char*, int) { return fail(s, IFX_ERR_INVALID, "multi-GPU not built yet"); }

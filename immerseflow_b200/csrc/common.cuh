@@ -1,0 +1,93 @@
+// common.cuh — shared device/host definitions for the B200-native ImmerseFlow++ path.
+//
+// HBM layout.  Every cell-centred field of a slab is one padded 2-D array:
+//     element (i, jl)  ->  base[ jl*pitch + IFX_PADL + i ],   i = 0..nx-1 (ghost-inclusive),
+//     jl = local row, global row j = j0 + jl.
+// IFX_PADL = 15 puts the first interior column (i = 1) on a 128-byte boundary and pitch is a
+// multiple of 16 doubles, so a warp reading 64 consecutive interior columns as double2 touches
+// exactly four full 128-B lines.  The reference's unpadded id = i + j*nx layout
+// (globalVariables.cuh) only exists at the C-ABI boundary (ifx_set_field / ifx_get_field).
+//
+// Arithmetic: this directory is compiled with -fmad=false.  Every fused multiply-add is written
+// out as fma() and mirrors the contraction nvcc emits for the reference kernels (read from the
+// reference's sm_100 PTX/SASS), so results are bit-identical to the reference CUDA build.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define IFX_PADL 15
+#define IFX_WARP 32
+
+// cell types (uint8).  The reference's iBlank is a double array, 1.0 fluid / 0.0 solid
+// (globalVariables.cuh:50-52); ghost cells are solid cells adjacent to fluid.
+#define IFX_SOLID 0
+#define IFX_FLUID 1
+#define IFX_GHOST 2
+
+namespace ifx {
+
+struct Layout {
+  int nx, ny;      // global ghost-inclusive sizes
+  int pitch;       // doubles per stored row
+  int nyl;         // stored local rows (owned interior rows + one halo/ghost row each side)
+  int j0;          // global row index of local row 0
+  int jb, je;      // owned interior rows, global, [jb, je)
+};
+
+__host__ __device__ __forceinline__ size_t lidx(const Layout& L, int i, int jl) {
+  return (size_t)jl * L.pitch + IFX_PADL + i;
+}
+
+// 1-D metric / coefficient tables (device pointers; x tables have nx entries, y tables ny entries,
+// indexed by GLOBAL i / j).  All values are computed on the device by k_build_metrics with the
+// reference's per-cell expressions, which only depend on i (x tables) or j (y tables).
+struct Metrics {
+  const double* dx;     // dx[i] = xf[i]-xf[i-1]; dx[0]=dx[1], dx[nx-1]=dx[nx-2]   (preSim.cu:329-355)
+  const double* dy;
+  const double* xc;     // cell centres incl. ghost centres                       (preSim.cu:294-307)
+  const double* yc;
+  const double* rcpx;   // rcpx[i] = 1/(dx[i]+dx[i+1]), i = 0..nx-2   (ADSolver.cu:66,173)
+  const double* rcpy;
+  const double* kxh;    // (dt/dx[i])*0.5                               (ADSolver.cu:66)
+  const double* kyh;
+  // predictor (ADSolver.cu:34-39), k = dt/Re
+  const double* ad_cE;  // k * 2/(dx_i (dx_i+dx_ip1))
+  const double* ad_cW;  // k * 2/(dx_i (dx_i+dx_im1))
+  const double* ad_px;  // fma(k, ax_p+ax_m, 1.0)
+  const double* ad_cN;
+  const double* ad_cS;
+  const double* ad_sy;  // ay_p+ay_m      -> cP = fma(k, ad_sy[j], ad_px[i])
+  // Poisson (PPESolver.cu:93-99)
+  const double* pp_cE;  // 2/(dx_i (dx_i+dx_ip1))
+  const double* pp_cW;
+  const double* pp_sx;  // ax_p+ax_m
+  const double* pp_cN;
+  const double* pp_cS;
+  const double* pp_sy;  // ay_p+ay_m      -> cP = -(pp_sx[i] + pp_sy[j])
+  double k;             // dt/Re
+  double dt;
+};
+
+// Device-resident loop control: lets the host enqueue sweeps blindly while the stop decision is
+// taken on the device by the last CTA of each sweep (no host round trip per iteration, unlike the
+// reference's blocking 8-byte D2H per Reduction(), preSim.cu:441).
+struct LoopCtl {
+  int iter;            // iterations whose residual has been evaluated
+  int done;            // 1: later launches exit immediately
+  int ambiguous;       // fused sum landed inside the rounding band of the tolerance
+  int hit_max;
+  unsigned ticket;     // CTA completion counter
+  int pad_;
+  double res0, res1;   // last evaluated residual sums (u,v) or (signed, abs) for PPE
+  double hist[2 * 64]; // first 64 iterations' residuals
+};
+
+#define IFX_MAX_PARTIALS_SLOTS 4
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+  return v;
+}
+
+}  // namespace ifx

@@ -1,0 +1,154 @@
+// kernels.cuh — kernel argument blocks, launch geometry and the fused residual reduction.
+#pragma once
+#include "common.cuh"
+
+namespace ifx {
+
+constexpr int AD_WARPS = 4;                 // warps per CTA, side by side in x
+constexpr int AD_THREADS = AD_WARPS * 32;   // 128 threads -> 256 columns per CTA
+constexpr int TILE_COLS = AD_WARPS * 64;
+
+// How a sweep's residual feeds the stop rule.
+struct ReduceCfg {
+  int eval_iter;    // index of the iterate whose residual this launch evaluates (0: no decision)
+  int itermax;
+  int decide;       // 0: leave the decision to the reference-order reduction kernels
+  int use_second;   // stop test on res0 + res1 (predictor: uRes + vRes, ADSolver.cu:315)
+  int test_abs;     // PPE: test res1 (= sum |r|) instead of the signed res0
+  int certify;      // flag decisions that fall inside the rounding band instead of taking them
+  double tol;
+  double band;      // relative half-width of the rounding band (times the abs-sum)
+};
+
+struct AdJacobiArgs {
+  Layout L;
+  Metrics M;
+  double* uC; double* vC;             // input iterate (its ghost ring is written, see kernel)
+  double* uT; double* vT;             // output iterate
+  const double* sx; const double* sy;
+  const uint8_t* celltype;
+  double* res_u; double* res_v;       // reference-layout residual arrays (WRITE_RES only)
+  double* partials;                   // 2 doubles per CTA
+  LoopCtl* ctl;
+  ReduceCfg rc;
+  double two_bc_u[4], two_bc_v[4];    // 2*bc for W, E, S, N
+  int rows_per_cta;
+  int force;                          // run even if ctl->done (reference-order re-evaluation)
+};
+
+struct AdSourceArgs {
+  Layout L;
+  Metrics M;
+  const double* u; const double* v;
+  const double* uf; const double* vf;
+  double* sx; double* sy;
+  double two_bc_u[4], two_bc_v[4];
+  int rows_per_cta;
+};
+
+struct PpeSweepArgs {
+  Layout L;
+  Metrics M;
+  double* pC;                         // input iterate
+  double* pT;                         // output iterate
+  const double* rhs;
+  const uint8_t* celltype;
+  double* res;                        // reference-layout residual array (WRITE_RES only)
+  double* partials;
+  LoopCtl* ctl;
+  ReduceCfg rc;
+  int rows_per_cta;
+  int force;
+};
+
+// ---------------------------------------------------------------------------------------------
+// Fused residual reduction: thread partials -> warp shuffle -> shared memory -> one pair of
+// doubles per CTA in global memory -> the LAST CTA to finish (atomic ticket) adds the CTA
+// partials in a fixed order and takes the stop decision on the device.  Deterministic: the
+// order depends only on the launch geometry, never on scheduling.
+// ---------------------------------------------------------------------------------------------
+template <int THREADS>
+__device__ __forceinline__ void block_reduce_and_decide(double r0, double r1, double* partials,
+                                                        LoopCtl* ctl, const ReduceCfg& rc,
+                                                        unsigned bid, unsigned nblocks) {
+  constexpr int NW = THREADS / 32;
+  __shared__ double sh[2][NW];
+  __shared__ int s_last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  r0 = warp_sum(r0);
+  r1 = warp_sum(r1);
+  if (lane == 0) { sh[0][warp] = r0; sh[1][warp] = r1; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = sh[0][0], b = sh[1][0];
+#pragma unroll
+    for (int w = 1; w < NW; ++w) { a += sh[0][w]; b += sh[1][w]; }
+    partials[2 * bid] = a;
+    partials[2 * bid + 1] = b;
+    __threadfence();
+    const unsigned t = atomicAdd(&ctl->ticket, 1u);
+    s_last = (t == nblocks - 1);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  double a = 0.0, b = 0.0;
+  for (unsigned k = threadIdx.x; k < nblocks; k += THREADS) {
+    a += __ldcg(partials + 2 * k);
+    b += __ldcg(partials + 2 * k + 1);
+  }
+  a = warp_sum(a);
+  b = warp_sum(b);
+  __syncthreads();
+  if (lane == 0) { sh[0][warp] = a; sh[1][warp] = b; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    a = sh[0][0]; b = sh[1][0];
+#pragma unroll
+    for (int w = 1; w < NW; ++w) { a += sh[0][w]; b += sh[1][w]; }
+    ctl->ticket = 0;
+    ctl->res0 = a;
+    ctl->res1 = b;
+    if (rc.eval_iter >= 1) {
+      if (rc.eval_iter <= 64) { ctl->hist[2 * (rc.eval_iter - 1)] = a; ctl->hist[2 * (rc.eval_iter - 1) + 1] = b; }
+      if (rc.decide) {
+        ctl->iter = rc.eval_iter;
+        const double S = rc.use_second ? a + b : (rc.test_abs ? b : a);
+        const double A = rc.use_second ? S : b;           // sum of magnitudes
+        const bool at_max = rc.eval_iter >= rc.itermax;
+        if (rc.certify && !at_max && fabs(S - rc.tol) <= rc.band * A) {
+          ctl->ambiguous = 1;
+          ctl->done = 1;
+        } else if (!(S > rc.tol) || at_max) {
+          ctl->hit_max = (S > rc.tol) ? 1 : 0;
+          ctl->done = 1;
+        }
+      }
+    }
+    __threadfence();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Host-side launchers.  Every __global__ is launched from the translation unit that defines it.
+// ---------------------------------------------------------------------------------------------
+// kernels_ad.cu
+cudaError_t launch_ad_jacobi(const AdJacobiArgs& a, dim3 grid, cudaStream_t st, bool write_res, bool has_gc);
+enum AdSourceVariant { SRC_REF_VF_ZERO = 0, SRC_REF_VF_ARRAY = 1, SRC_FACES = 2 };
+cudaError_t launch_ad_source(const AdSourceArgs& a, dim3 grid, cudaStream_t st, AdSourceVariant v);
+cudaError_t launch_copy_ring(const Layout& L, const double* s0, double* d0, const double* s1, double* d1,
+                             cudaStream_t st);
+// kernels_ppe.cu
+cudaError_t launch_ppe_sweep(const PpeSweepArgs& a, dim3 grid, cudaStream_t st, bool laplace_ref, bool write_res,
+                             bool has_gc);
+cudaError_t launch_set_pressure_bc_ref(const Layout& L, double* p0, double* p1, cudaStream_t st);
+// kernels_reduce.cu — the reference's summation order (preSim.cu:12-50, 376-441)
+cudaError_t launch_reduce6(const double* in, size_t n, double* partial, double* out, cudaStream_t st);
+cudaError_t launch_decide_exact(LoopCtl* ctl, const double* sums, const ReduceCfg& rc, cudaStream_t st);
+// kernels_misc.cu / kernels_ic.cu
+cudaError_t launch_init_vortex(const Layout& L, const double* xc, const double* yc, double* u, double* v, double* p,
+                               cudaStream_t st);
+cudaError_t launch_fill_u8(uint8_t* p, size_t n, uint8_t v, cudaStream_t st);
+cudaError_t launch_pack_u8(const Layout& L, const uint8_t* padded, double* dense, int raw, cudaStream_t st);
+
+}  // namespace ifx

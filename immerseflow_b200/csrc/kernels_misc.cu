@@ -1,0 +1,47 @@
+// kernels_misc.cu — layout conversion between the reference's dense id = i + j*nx arrays (C-ABI
+// boundary) and the padded HBM layout, plus small fills.
+#include "kernels.cuh"
+
+namespace ifx {
+
+static __global__ void k_fill_u8(uint8_t* p, size_t n, uint8_t v) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; t < n; t += stride) p[t] = v;
+}
+
+// dense rows [j_lo, j_hi) (global) <-> padded local rows; dense points at global row j_lo.
+static __global__ void k_pack(Layout L, const double* __restrict__ padded, double* __restrict__ dense,
+                       int j_lo, int j_hi) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = j_lo + blockIdx.y;
+  if (i < L.nx && j < j_hi) dense[(size_t)(j - j_lo) * L.nx + i] = padded[lidx(L, i, j - L.j0)];
+}
+static __global__ void k_unpack(Layout L, const double* __restrict__ dense, double* __restrict__ padded,
+                         int j_lo, int j_hi) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = j_lo + blockIdx.y;
+  if (i < L.nx && j < j_hi) padded[lidx(L, i, j - L.j0)] = dense[(size_t)(j - j_lo) * L.nx + i];
+}
+// cell types -> doubles.  raw = 0: the reference's iBlank (1.0 fluid, 0.0 otherwise); raw = 1: type code.
+static __global__ void k_pack_u8(Layout L, const uint8_t* __restrict__ padded, double* __restrict__ dense,
+                          int j_lo, int j_hi, int raw) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = j_lo + blockIdx.y;
+  if (i < L.nx && j < j_hi) {
+    const uint8_t c = padded[lidx(L, i, j - L.j0)];
+    dense[(size_t)(j - j_lo) * L.nx + i] = raw ? (double)c : (c == IFX_FLUID ? 1.0 : 0.0);
+  }
+}
+
+cudaError_t launch_fill_u8(uint8_t* p, size_t n, uint8_t v, cudaStream_t st) {
+  k_fill_u8<<<296, 256, 0, st>>>(p, n, v);
+  return cudaGetLastError();
+}
+cudaError_t launch_pack_u8(const Layout& L, const uint8_t* padded, double* dense, int raw, cudaStream_t st) {
+  dim3 g((L.nx + 127) / 128, L.nyl);
+  k_pack_u8<<<g, 128, 0, st>>>(L, padded, dense, L.j0, L.j0 + L.nyl, raw);
+  return cudaGetLastError();
+}
+
+}  // namespace ifx

@@ -1,0 +1,97 @@
+// solver.h — host-side state of one slab (one GPU).  Replaces `struct ImmerseFlow`
+// (reference src/header/globalVariables.cuh:70-88); owns every device allocation for the life of
+// the handle (the reference mallocs/frees 11 N-sized arrays per step, ADSolver.cu:275-287,382-394).
+#pragma once
+#include "../../include/immerseflow_c.h"
+#include "kernels.cuh"
+
+#include <string>
+#include <vector>
+
+struct GhostCells {
+  int count = 0, capacity = 0;
+  int* cell = nullptr;        // padded-layout offset of each ghost cell (sorted by reference id)
+  int* ref_id = nullptr;      // reference id = i + j*nx
+  int* stencil = nullptr;     // 4 padded offsets per ghost cell
+  int* stencil_ref = nullptr; // 4 reference ids
+  double* w_dir = nullptr;    // 4 weights + 1 constant multiplier, Dirichlet closure (u, v)
+  double* w_neu = nullptr;    // 4 weights, Neumann closure (p)
+  double* bi = nullptr;       // body intercept x,y
+  double* ip = nullptr;       // image point x,y
+  int* body = nullptr;        // owning body index
+};
+
+struct ifx_solver {
+  ifx_input in{};
+  ifx_options opt{};
+  ifx::Layout L{};
+  ifx::Metrics M{};
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  bool initialized = false;
+
+  size_t field_elems = 0;            // doubles per padded field allocation
+  double* u[2] = {nullptr, nullptr};
+  double* v[2] = {nullptr, nullptr};
+  double* p[2] = {nullptr, nullptr};
+  int cur_uv = 0, cur_p = 0;
+  double *sx = nullptr, *sy = nullptr, *rhs = nullptr, *uf = nullptr, *vf = nullptr;
+  uint8_t* celltype = nullptr;
+  bool faces_valid = false;          // uf/vf hold projected face velocities (FULL mode)
+
+  // reduction scratch
+  double* partials = nullptr;        // 2 doubles per CTA
+  size_t partials_cap = 0;
+  ifx::LoopCtl* ctl = nullptr;       // device
+  ifx::LoopCtl* h_ctl = nullptr;     // pinned host mirror
+  double *res_a = nullptr, *res_b = nullptr;   // reference-layout residual arrays (lazy)
+  double* red_partial = nullptr;     // level-1 partials for the reference-order reduction
+  double* red_out = nullptr;         // 2 doubles
+
+  std::vector<double*> tables;       // device 1-D metric tables (freed in destroy)
+  std::vector<double> h_xc, h_yc, h_dx, h_dy;
+
+  // immersed boundary
+  int nbodies = 0;
+  std::vector<int> h_body_off;
+  std::vector<double> h_xm, h_ym, h_ub, h_vb;
+  int *d_body_off = nullptr;
+  double *d_xm = nullptr, *d_ym = nullptr, *d_ub = nullptr, *d_vb = nullptr;
+  bool bodies_dirty = false;
+  bool has_gc = false;
+  GhostCells gc;
+  int* d_counters = nullptr;
+  int* d_rowcount = nullptr;
+
+  // multi-GPU exchange
+  void* xchg = nullptr;              // this rank's exchange segment (IPC-exported)
+  size_t xchg_bytes = 0;
+  void* peer_lo = nullptr;           // mapped segment of rank-1 / rank+1
+  void* peer_hi = nullptr;
+  std::vector<void*> peer_all;
+
+  int last_ad_iters = 5;
+  cudaEvent_t ev[8] = {};
+  long long launches = 0;
+  std::string err;
+};
+
+namespace ifx {
+int fail(ifx_solver* s, int code, const std::string& msg);
+}
+
+#define IFX_CUDA(s, call)                                                                      \
+  do {                                                                                         \
+    cudaError_t e__ = (call);                                                                  \
+    if (e__ != cudaSuccess)                                                                    \
+      return ifx::fail((s), IFX_ERR_CUDA,                                                      \
+                       std::string(#call) + ": " + cudaGetErrorString(e__) + " (" + __FILE__ + \
+                           ":" + std::to_string(__LINE__) + ")");                              \
+  } while (0)
+
+#define IFX_LAUNCH_CHECK(s)                   \
+  do {                                        \
+    (s)->launches++;                          \
+    IFX_CUDA((s), cudaGetLastError());        \
+  } while (0)

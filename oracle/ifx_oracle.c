@@ -322,6 +322,16 @@ int orc_ADsolver(int nx, int ny, const double* dx, const double* dy, double dt, 
                  int AD_itermax, const double* iblank,
                  double* u, double* v, double* uf, double* vf,
                  int vf_mode, double* res_hist) {
+  return orc_ADsolver_tol(nx, ny, dx, dy, dt, Re, AD_itermax, iblank, u, v, uf, vf, vf_mode, res_hist,
+                          pow(10.0, -6.0));                                    /* :315 */
+}
+
+/* Same loop with the tolerance as a parameter (the reference hard-codes pow(10,-6)); lets the tests
+ * place the tolerance exactly on a residual to exercise the stop rule at the rounding boundary. */
+int orc_ADsolver_tol(int nx, int ny, const double* dx, const double* dy, double dt, double Re,
+                     int AD_itermax, const double* iblank,
+                     double* u, double* v, double* uf, double* vf,
+                     int vf_mode, double* res_hist, double tol) {
   const size_t N = (size_t)nx * ny;
   const int tpb = 256, bpg = ((int)N + tpb - 1) / tpb;               /* preSim.cu:190-193 */
   double* mem = (double*)malloc(sizeof(double) * N * 11);
@@ -343,7 +353,7 @@ int orc_ADsolver(int nx, int ny, const double* dx, const double* dy, double dt, 
       }
   orc_ADSource(nx, ny, dx, dy, dt, uc, vc, uf, vf, sx, sy);                     /* :308 */
 
-  while (uResidual + vResidual > pow(10.0, -6.0) && iter < AD_itermax) {        /* :315 */
+  while (uResidual + vResidual > tol && iter < AD_itermax) {                     /* :315 */
     orc_set_velocity_BC(nx, ny, uc, vc);                                        /* :317 */
     orc_Compute_velf(nx, ny, dx, dy, uc, vc, uf, vf, vf_mode);                  /* :321 */
     orc_ADsolver_kernel(nx, ny, c, cxm, cxp, cym, cyp, iblank, uc, uTemp, sx);  /* :326 */
@@ -451,6 +461,11 @@ void orc_Compute_Residual(int nx, int ny,
  * ---------------------------------------------------------------------------------------- */
 int orc_PPESolver(int nx, int ny, const double* dx, const double* dy,
                   int PPE_itermax, double* p, double* final_residual) {
+  return orc_PPESolver_tol(nx, ny, dx, dy, PPE_itermax, p, final_residual, pow(10.0, -6.0));   /* :172 */
+}
+
+int orc_PPESolver_tol(int nx, int ny, const double* dx, const double* dy,
+                      int PPE_itermax, double* p, double* final_residual, double tol) {
   const size_t N = (size_t)nx * ny;
   const int tpb = 256, bpg = ((int)N + tpb - 1) / tpb;
   double* mem = (double*)calloc(N * 7, sizeof(double));
@@ -461,7 +476,7 @@ int orc_PPESolver(int nx, int ny, const double* dx, const double* dy,
   orc_set_pressure_BC(nx, ny, pc);                                         /* :164 */
   double Residual = 1.0;
   int iter = 0;
-  while (Residual > pow(10.0, -6.0) && iter < PPE_itermax) {               /* :172 */
+  while (Residual > tol && iter < PPE_itermax) {                           /* :172 */
     orc_jacobiIteration(nx, ny, cP, cxm, cxp, cym, cyp, pc, pTemp);        /* :174 */
     double* t = pc; pc = pTemp; pTemp = t;                                 /* :178-180 */
     orc_Compute_Residual(nx, ny, cP, cxm, cxp, cym, cyp, pc, pResidue);    /* :182 */

@@ -79,6 +79,10 @@ int orc_ADsolver(int nx, int ny, const double* dx, const double* dy, double dt, 
                  int AD_itermax, const double* iblank,
                  double* u, double* v, double* uf, double* vf,
                  int vf_mode, double* res_hist);
+int orc_ADsolver_tol(int nx, int ny, const double* dx, const double* dy, double dt, double Re,
+                     int AD_itermax, const double* iblank,
+                     double* u, double* v, double* uf, double* vf,
+                     int vf_mode, double* res_hist, double tol);
 
 /* ---- a11-a14: Laplace-Jacobi PPE as written, PPESolver.cu:13-104,137-197 ---------------- */
 void orc_calculatePPECoefficients(int nx, int ny, const double* dx, const double* dy,
@@ -96,6 +100,8 @@ void orc_Compute_Residual(int nx, int ny,
 /* Returns the sweep count; p updated in place; *final_residual = last signed sum. */
 int orc_PPESolver(int nx, int ny, const double* dx, const double* dy,
                   int PPE_itermax, double* p, double* final_residual);
+int orc_PPESolver_tol(int nx, int ny, const double* dx, const double* dy,
+                      int PPE_itermax, double* p, double* final_residual, double tol);
 
 /* ---- b: Tecplot writer, postSim.cu:41-66 ---------------------------------------------- */
 int orc_write_results_to_file(const double* x, const double* y, const double* data,
