@@ -22,7 +22,9 @@ k_ppe_sweep(PpeSweepArgs a) {
   const int jlast = min(jfirst + a.rows_per_cta, L.je);
   const int nxm2 = L.nx - 2, nym2 = L.ny - 2;
   const bool act0 = i <= nxm2, act1 = i + 1 <= nxm2;
-  const int ic = act0 ? i : 1;
+  // Out-of-range lanes are clamped to a valid address; the lane sitting on the E ghost column must load it for
+  // real: its pC.x is the east neighbour (stored Dirichlet ring) of the last interior column next door.
+  const int ic = (act0 || (LAPLACE_REF && i == L.nx - 1)) ? i : 1;
 
   const double cE0 = a.M.pp_cE[ic], cW0 = a.M.pp_cW[ic], sx0 = a.M.pp_sx[ic];
   const double cE1 = a.M.pp_cE[ic + 1], cW1 = a.M.pp_cW[ic + 1], sx1 = a.M.pp_sx[ic + 1];
