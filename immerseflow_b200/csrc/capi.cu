@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -116,18 +117,26 @@ static int build_metrics(ifx_solver* s, const double* xf, const double* yf) {
   return IFX_OK;
 }
 
-static int rows_per_cta_for(const ifx_solver* s) {
+// columns per CTA tile of the sweep kernels (mode 0: Poisson, 2: predictor)
+static int tile_cols_for(const ifx_solver* s, int mode) {
+  const int tune = (mode == 2) ? s->tune_ad : s->tune_ppe;
+  if (s->kernel_variant == 4) return v4_tile_cols(mode, tune);
+  return s->kernel_variant == 3 ? v3_tile_cols(mode, tune) : TILE_COLS;
+}
+
+static int rows_per_cta_for(const ifx_solver* s, int mode) {
+  if (s->rows_override > 0) return s->rows_override;
   // enough CTAs for >= ~6 per SM when the grid allows it, tall tiles (less halo re-read) otherwise
-  const int nxi = s->L.nx - 2, nyi = s->L.je - s->L.jb;
-  const int gx = (nxi + TILE_COLS - 1) / TILE_COLS;
+  const int nxi = s->L.nx - 2, nyi = s->L.je - s->L.jb, tw = tile_cols_for(s, mode);
+  const int gx = (nxi + tw - 1) / tw;
   int ry = 64;
   while (ry > 4 && (long long)gx * ((nyi + ry - 1) / ry) < 148LL * 6) ry >>= 1;
   return ry;
 }
 
-static dim3 tile_grid(const ifx_solver* s, int ry) {
-  const int nxi = s->L.nx - 2, nyi = s->L.je - s->L.jb;
-  return dim3((nxi + TILE_COLS - 1) / TILE_COLS, (nyi + ry - 1) / ry, 1);
+static dim3 tile_grid(const ifx_solver* s, int ry, int mode) {
+  const int nxi = s->L.nx - 2, nyi = s->L.je - s->L.jb, tw = tile_cols_for(s, mode);
+  return dim3((nxi + tw - 1) / tw, (nyi + ry - 1) / ry, 1);
 }
 
 static int ensure_partials(ifx_solver* s, size_t nblocks) {
@@ -177,7 +186,7 @@ static void fill_bc(const ifx_solver* s, double* two_u, double* two_v) {
 static double rounding_band(const ifx_solver* s, size_t nblocks, int rows_per_cta) {
   const double N = (double)s->L.nx * s->L.ny;
   const double d_ref = 10.0 + std::ceil(N / 256.0 / 512.0) + 1.0 + 8.0 + 2.0;
-  const double d_fused = 2.0 * rows_per_cta + 5.0 + AD_WARPS + std::ceil((double)nblocks / AD_THREADS) + 5.0 + AD_WARPS + 2.0;
+  const double d_fused = 8.0 * rows_per_cta + 5.0 + AD_WARPS + std::ceil((double)nblocks / AD_THREADS) + 5.0 + AD_WARPS + 2.0;
   return 2.0 * (d_ref + d_fused) * 1.1102230246251565e-16;
 }
 
@@ -209,6 +218,10 @@ extern "C" int ifx_create(const ifx_input* in, const double* xf, const double* y
   s->in = *in;
   s->opt = opt;
   s->device = opt.device;
+  if (const char* e = std::getenv("IFX_KERNEL_VARIANT")) { const int v = std::atoi(e); if (v >= 1 && v <= 4) s->kernel_variant = v; }
+  if (const char* e = std::getenv("IFX_TUNE_AD")) s->tune_ad = std::atoi(e);
+  if (const char* e = std::getenv("IFX_TUNE_PPE")) s->tune_ppe = std::atoi(e);
+  if (const char* e = std::getenv("IFX_ROWS_PER_CTA")) s->rows_override = std::atoi(e);
   auto bail = [&](int code) { g_create_error = s->err; ifx_destroy(s); return code; };
 
   cudaError_t e = cudaSetDevice(s->device);
@@ -445,7 +458,10 @@ extern "C" int ifx_reduce_sum(ifx_solver* s, const double* host, size_t n, doubl
 // ------------------------------------------------------------------------------------------------
 static int launch_ad_jacobi(ifx_solver* s, AdJacobiArgs& a, dim3 grid, bool write_res) {
   s->launches++;
-  IFX_CUDA(s, ifx::launch_ad_jacobi(a, grid, s->stream, write_res, s->has_gc));
+  if (s->kernel_variant == 1) IFX_CUDA(s, ifx::launch_ad_jacobi(a, grid, s->stream, write_res, s->has_gc));
+  else if (s->kernel_variant == 2) IFX_CUDA(s, ifx::launch_ad_jacobi_v2(a, grid, s->stream, write_res, s->has_gc, s->tune_ad));
+  else if (s->kernel_variant == 3) IFX_CUDA(s, ifx::launch_ad_jacobi_v3(a, grid, s->stream, write_res, s->has_gc, s->tune_ad));
+  else IFX_CUDA(s, ifx::launch_ad_jacobi_v4(a, grid, s->stream, write_res, s->tune_ad));
   return IFX_OK;
 }
 
@@ -471,9 +487,11 @@ extern "C" int ifx_ad_solve(ifx_solver* s, ifx_step_stats* st) {
   const bool exact = s->opt.reduce_mode == IFX_REDUCE_REFERENCE;
   const bool full = s->opt.compat == IFX_COMPAT_FULL;
   const int itermax = s->in.AD_itermax;
-  const int ry = rows_per_cta_for(s);
-  const dim3 grid = tile_grid(s, ry);
+  const int ry = rows_per_cta_for(s, 2);
+  const dim3 grid = tile_grid(s, ry, 2);
   const size_t nblocks = (size_t)grid.x * grid.y;
+  // the source pass always uses the 256-column direct-load tiles
+  const dim3 grid_src((L.nx - 2 + TILE_COLS - 1) / TILE_COLS, grid.y, 1);
   int rc = ensure_partials(s, nblocks);
   if (rc != IFX_OK) return rc;
   if (exact && (rc = ensure_exact_buffers(s)) != IFX_OK) return rc;
@@ -491,9 +509,9 @@ extern "C" int ifx_ad_solve(ifx_solver* s, ifx_step_stats* st) {
   sa.rows_per_cta = ry;
   if (full) {
     if (!s->faces_valid) return fail(s, IFX_ERR_STATE, "face velocities not initialised (call ifx_step / ifx_iblank_update)");
-    IFX_CUDA(s, launch_ad_source(sa, grid, s->stream, SRC_FACES));
+    IFX_CUDA(s, launch_ad_source(sa, grid_src, s->stream, SRC_FACES));
   } else if (L.nx <= L.ny) {
-    IFX_CUDA(s, launch_ad_source(sa, grid, s->stream, SRC_REF_VF_ZERO));     // vf == 0 (App. A Q2)
+    IFX_CUDA(s, launch_ad_source(sa, grid_src, s->stream, SRC_REF_VF_ZERO));     // vf == 0 (App. A Q2)
   } else {
     return fail(s, IFX_ERR_INVALID, "IFX_COMPAT_REFERENCE with nx > ny: the reference overruns its vf allocation "
                                     "(preSim.cu:153, ADSolver.cu:179-186); use IFX_COMPAT_FULL");
@@ -578,7 +596,10 @@ extern "C" int ifx_ad_solve(ifx_solver* s, ifx_step_stats* st) {
 // ------------------------------------------------------------------------------------------------
 static int launch_ppe_sweep(ifx_solver* s, PpeSweepArgs& a, dim3 grid, bool laplace_ref, bool write_res) {
   s->launches++;
-  IFX_CUDA(s, ifx::launch_ppe_sweep(a, grid, s->stream, laplace_ref, write_res, s->has_gc));
+  if (s->kernel_variant == 1) IFX_CUDA(s, ifx::launch_ppe_sweep(a, grid, s->stream, laplace_ref, write_res, s->has_gc));
+  else if (s->kernel_variant == 2) IFX_CUDA(s, ifx::launch_ppe_sweep_v2(a, grid, s->stream, laplace_ref, write_res, s->has_gc, s->tune_ppe));
+  else if (s->kernel_variant == 3) IFX_CUDA(s, ifx::launch_ppe_sweep_v3(a, grid, s->stream, laplace_ref, write_res, s->has_gc, s->tune_ppe));
+  else IFX_CUDA(s, ifx::launch_ppe_sweep_v4(a, grid, s->stream, laplace_ref, write_res, s->tune_ppe));
   return IFX_OK;
 }
 
@@ -589,8 +610,8 @@ extern "C" int ifx_ppe_solve(ifx_solver* s, ifx_step_stats* st) {
   const bool exact = s->opt.reduce_mode == IFX_REDUCE_REFERENCE;
   const bool laplace_ref = s->opt.compat == IFX_COMPAT_REFERENCE;
   const int itermax = s->in.PPE_itermax;
-  const int ry = rows_per_cta_for(s);
-  const dim3 grid = tile_grid(s, ry);
+  const int ry = rows_per_cta_for(s, 0);
+  const dim3 grid = tile_grid(s, ry, 0);
   const size_t nblocks = (size_t)grid.x * grid.y;
   int rc = ensure_partials(s, nblocks);
   if (rc != IFX_OK) return rc;

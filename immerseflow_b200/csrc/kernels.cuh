@@ -142,6 +142,19 @@ cudaError_t launch_copy_ring(const Layout& L, const double* s0, double* d0, cons
 cudaError_t launch_ppe_sweep(const PpeSweepArgs& a, dim3 grid, cudaStream_t st, bool laplace_ref, bool write_res,
                              bool has_gc);
 cudaError_t launch_set_pressure_bc_ref(const Layout& L, double* p0, double* p1, cudaStream_t st);
+// kernels_v2.cu — the same sweeps behind a cp.async.bulk + mbarrier row pipeline (default variant)
+cudaError_t launch_ad_jacobi_v2(const AdJacobiArgs& a, dim3 grid, cudaStream_t st, bool write_res, bool has_gc, int tune);
+cudaError_t launch_ppe_sweep_v2(const PpeSweepArgs& a, dim3 grid, cudaStream_t st, bool laplace_ref, bool write_res,
+                                bool has_gc, int tune);
+// kernels_v3.cu — pipeline + rows read from the smem ring, 4-8 columns per thread, predictor split by field (default)
+cudaError_t launch_ad_jacobi_v3(const AdJacobiArgs& a, dim3 grid, cudaStream_t st, bool write_res, bool has_gc, int tune);
+cudaError_t launch_ppe_sweep_v3(const PpeSweepArgs& a, dim3 grid, cudaStream_t st, bool laplace_ref, bool write_res,
+                                bool has_gc, int tune);
+int v3_tile_cols(int mode /*0,1: Poisson, 2: predictor*/, int tune);
+// kernels_v4.cu — v3 + lean interior path, in-line shared-reciprocal division, smem row tables (default)
+cudaError_t launch_ad_jacobi_v4(const AdJacobiArgs& a, dim3 grid, cudaStream_t st, bool write_res, int tune);
+cudaError_t launch_ppe_sweep_v4(const PpeSweepArgs& a, dim3 grid, cudaStream_t st, bool laplace_ref, bool write_res, int tune);
+int v4_tile_cols(int mode /*0,1: Poisson, 2: predictor*/, int tune);
 // kernels_reduce.cu — the reference's summation order (preSim.cu:12-50, 376-441)
 cudaError_t launch_reduce6(const double* in, size_t n, double* partial, double* out, cudaStream_t st);
 cudaError_t launch_decide_exact(LoopCtl* ctl, const double* sums, const ReduceCfg& rc, cudaStream_t st);

@@ -10,25 +10,9 @@
 // Coefficients are separable and time-invariant: 1-D tables instead of the
 // reference's five N-sized arrays rebuilt every step (ADSolver.cu:275-291).
 #include "kernels.cuh"
+#include "stencil_math.cuh"
 
 namespace ifx {
-
-// ---------------------------------------------------------------------------------------------
-// Per-row coefficient bundle for the 5-point predictor stencil.
-// ---------------------------------------------------------------------------------------------
-struct RowC { double cN, cS, sy; };
-
-// One cell of ADusolver_kernel/ADvsolver_kernel (ADSolver.cu:91-94, :112-115):
-//   t = fma(cS,qS, fma(cN,qN, fma(cW,qW, fma(cE,qE, s))));  qnew = (iBlank*t)/cP
-__device__ __forceinline__ double jac_cell(double s, double cE, double qE, double cW, double qW,
-                                           double cN, double qN, double cS, double qS,
-                                           double ib, double cP) {
-  double t = fma(cE, qE, s);
-  t = fma(cW, qW, t);
-  t = fma(cN, qN, t);
-  t = fma(cS, qS, t);
-  return (ib * t) / cP;
-}
 
 // ---------------------------------------------------------------------------------------------
 // k_ad_jacobi: one point-Jacobi iteration of (I - dt/Re Lap) q = s for q = u and q = v.

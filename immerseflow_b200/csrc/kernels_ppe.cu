@@ -8,6 +8,7 @@
 // evaluates the residual of iterate m — the one the reference tests after sweep m — so the
 // stop decision is identical; when it fires, iterate m is still intact in the input buffer.
 #include "kernels.cuh"
+#include "stencil_math.cuh"
 
 namespace ifx {
 
@@ -77,23 +78,21 @@ k_ppe_sweep(PpeSweepArgs a) {
 
     double2 pn, r;
     if (LAPLACE_REF) {
-      // jacobiIteration (PPESolver.cu:24-27): t = pW*cW; fma(pE,cE,t); fma(pN,cN,t); fma(pS,cS,t); (-t)/cP
-      double t0 = pW0 * cW0; t0 = fma(pE0, cE0, t0); t0 = fma(pNn.x, cN, t0); t0 = fma(pSs.x, cS, t0);
-      double t1 = pW1 * cW1; t1 = fma(pE1, cE1, t1); t1 = fma(pNn.y, cN, t1); t1 = fma(pSs.y, cS, t1);
-      pn.x = (-t0) / cP0; pn.y = (-t1) / cP1;
-      // Compute_Residual (PPESolver.cu:42-46): q = pE*cE; fma(p,cP,q); fma(pW,cW,q); fma(pN,cN,q); fma(pS,cS,q)
-      double q0 = pE0 * cE0; q0 = fma(pC.x, cP0, q0); q0 = fma(pW0, cW0, q0); q0 = fma(pNn.x, cN, q0); q0 = fma(pSs.x, cS, q0);
-      double q1 = pE1 * cE1; q1 = fma(pC.y, cP1, q1); q1 = fma(pW1, cW1, q1); q1 = fma(pNn.y, cN, q1); q1 = fma(pSs.y, cS, q1);
+      const double t0 = ppe_offdiag(pW0, cW0, pE0, cE0, pNn.x, cN, pSs.x, cS);
+      const double t1 = ppe_offdiag(pW1, cW1, pE1, cE1, pNn.y, cN, pSs.y, cS);
+      pn.x = (-t0) / cP0; pn.y = (-t1) / cP1;                          // PPESolver.cu:24-27
+      const double q0 = ppe_apply(pC.x, cP0, pW0, cW0, pE0, cE0, pNn.x, cN, pSs.x, cS);   // :42-46
+      const double q1 = ppe_apply(pC.y, cP1, pW1, cW1, pE1, cE1, pNn.y, cN, pSs.y, cS);
       r.x = act0 ? q0 : 0.0; r.y = act1 ? q1 : 0.0;
       if (act1) *reinterpret_cast<double2*>(a.pT + o) = pn;
       else if (act0) a.pT[o] = pn.x;
     } else {
       const double2 f = *reinterpret_cast<const double2*>(a.rhs + o);
       const uchar2 ct = *reinterpret_cast<const uchar2*>(a.celltype + o);
-      double t0 = pW0 * cW0; t0 = fma(pE0, cE0, t0); t0 = fma(pNn.x, cN, t0); t0 = fma(pSs.x, cS, t0);
-      double t1 = pW1 * cW1; t1 = fma(pE1, cE1, t1); t1 = fma(pNn.y, cN, t1); t1 = fma(pSs.y, cS, t1);
-      double q0 = pE0 * cE0; q0 = fma(pC.x, cP0, q0); q0 = fma(pW0, cW0, q0); q0 = fma(pNn.x, cN, q0); q0 = fma(pSs.x, cS, q0);
-      double q1 = pE1 * cE1; q1 = fma(pC.y, cP1, q1); q1 = fma(pW1, cW1, q1); q1 = fma(pNn.y, cN, q1); q1 = fma(pSs.y, cS, q1);
+      const double t0 = ppe_offdiag(pW0, cW0, pE0, cE0, pNn.x, cN, pSs.x, cS);
+      const double t1 = ppe_offdiag(pW1, cW1, pE1, cE1, pNn.y, cN, pSs.y, cS);
+      const double q0 = ppe_apply(pC.x, cP0, pW0, cW0, pE0, cE0, pNn.x, cN, pSs.x, cS);
+      const double q1 = ppe_apply(pC.y, cP1, pW1, cW1, pE1, cE1, pNn.y, cN, pSs.y, cS);
       const bool fl0 = ct.x == IFX_FLUID, fl1 = ct.y == IFX_FLUID;
       pn.x = fl0 ? (f.x - t0) / cP0 : pC.x;      // solid cells keep their value in both buffers
       pn.y = fl1 ? (f.y - t1) / cP1 : pC.y;

@@ -71,6 +71,11 @@ struct ifx_solver {
   void* peer_hi = nullptr;
   std::vector<void*> peer_all;
 
+  int kernel_variant = 4;            // 1: register-rolled direct loads, 2: bulk-copy pipeline + rolling,
+                                     // 3: pipeline + smem-resident rows, field-split predictor,
+                                     // 4: 3 + lean interior path / shared-reciprocal division (IFX_KERNEL_VARIANT)
+  int tune_ad = 0, tune_ppe = 0;     // pipeline geometry selectors (IFX_TUNE_AD / IFX_TUNE_PPE)
+  int rows_override = 0;             // IFX_ROWS_PER_CTA
   int last_ad_iters = 5;
   cudaEvent_t ev[8] = {};
   long long launches = 0;
