@@ -28,8 +28,6 @@ SOURCES = [
     ("capi_full.cu", True),
     ("kernels_ad.cu", True),
     ("kernels_ppe.cu", True),
-    ("kernels_v2.cu", True),
-    ("kernels_v3.cu", True),
     ("kernels_v4.cu", True),
     ("kernels_reduce.cu", True),
     ("kernels_misc.cu", True),

@@ -120,11 +120,10 @@ static int build_metrics(ifx_solver* s, const double* xf, const double* yf) {
 // columns per CTA tile of the sweep kernels (mode 0: Poisson, 2: predictor)
 static int tile_cols_for(const ifx_solver* s, int mode) {
   const int tune = (mode == 2) ? s->tune_ad : s->tune_ppe;
-  if (s->kernel_variant == 4) return v4_tile_cols(mode, tune);
-  return s->kernel_variant == 3 ? v3_tile_cols(mode, tune) : TILE_COLS;
+  return s->kernel_variant == 4 ? v4_tile_cols(mode, tune) : TILE_COLS;
 }
 
-static int rows_per_cta_for(const ifx_solver* s, int mode) {
+int ifx::rows_per_cta_for(const ifx_solver* s, int mode) {
   if (s->rows_override > 0) return s->rows_override;
   // enough CTAs for >= ~6 per SM when the grid allows it, tall tiles (less halo re-read) otherwise
   const int nxi = s->L.nx - 2, nyi = s->L.je - s->L.jb, tw = tile_cols_for(s, mode);
@@ -134,12 +133,12 @@ static int rows_per_cta_for(const ifx_solver* s, int mode) {
   return ry;
 }
 
-static dim3 tile_grid(const ifx_solver* s, int ry, int mode) {
+dim3 ifx::tile_grid(const ifx_solver* s, int ry, int mode) {
   const int nxi = s->L.nx - 2, nyi = s->L.je - s->L.jb, tw = tile_cols_for(s, mode);
   return dim3((nxi + tw - 1) / tw, (nyi + ry - 1) / ry, 1);
 }
 
-static int ensure_partials(ifx_solver* s, size_t nblocks) {
+int ifx::ensure_partials(ifx_solver* s, size_t nblocks) {
   if (nblocks <= s->partials_cap) return IFX_OK;
   if (s->partials) cudaFree(s->partials);
   s->partials = nullptr;
@@ -148,7 +147,7 @@ static int ensure_partials(ifx_solver* s, size_t nblocks) {
   return IFX_OK;
 }
 
-static int ensure_exact_buffers(ifx_solver* s) {
+int ifx::ensure_exact_buffers(ifx_solver* s) {
   if (s->res_a) return IFX_OK;
   if (s->opt.nranks != 1)
     return fail(s, IFX_ERR_INVALID, "reference-order reduction is single-GPU only");
@@ -162,19 +161,19 @@ static int ensure_exact_buffers(ifx_solver* s) {
 }
 
 // ImmerseFlow::Reduction (preSim.cu:376-445) on a device array of n doubles -> *out (device)
-static int reduce_reference_order(ifx_solver* s, const double* d_in, size_t n, double* d_out) {
+static int reduce_reference_order(ifx_solver* s, const double* d_in, size_t n, double* d_out, bool abs_values = false) {
   s->launches += 2;
-  IFX_CUDA(s, launch_reduce6(d_in, n, s->red_partial, d_out, s->stream));
+  IFX_CUDA(s, launch_reduce6(d_in, n, s->red_partial, d_out, s->stream, abs_values));
   return IFX_OK;
 }
 
-static int fetch_ctl(ifx_solver* s) {
+int ifx::fetch_ctl(ifx_solver* s) {
   IFX_CUDA(s, cudaMemcpyAsync(s->h_ctl, s->ctl, sizeof(LoopCtl), cudaMemcpyDeviceToHost, s->stream));
   IFX_CUDA(s, cudaStreamSynchronize(s->stream));
   return IFX_OK;
 }
 
-static void fill_bc(const ifx_solver* s, double* two_u, double* two_v) {
+void ifx::fill_bc(const ifx_solver* s, double* two_u, double* two_v) {
   const ifx_bc& b = s->opt.bc;
   two_u[0] = b.u_bc_w * 2.0; two_u[1] = b.u_bc_e * 2.0; two_u[2] = b.u_bc_s * 2.0; two_u[3] = b.u_bc_n * 2.0;
   two_v[0] = b.v_bc_w * 2.0; two_v[1] = b.v_bc_e * 2.0; two_v[2] = b.v_bc_s * 2.0; two_v[3] = b.v_bc_n * 2.0;
@@ -183,7 +182,7 @@ static void fill_bc(const ifx_solver* s, double* two_u, double* two_v) {
 // Half-width (relative to the sum of magnitudes) of the band inside which the fused summation order
 // and the reference's could disagree about `sum > tol`: gamma_d with d = the deepest chain of
 // additions either order applies to one term, times a safety factor of 2.
-static double rounding_band(const ifx_solver* s, size_t nblocks, int rows_per_cta) {
+double ifx::rounding_band(const ifx_solver* s, size_t nblocks, int rows_per_cta) {
   const double N = (double)s->L.nx * s->L.ny;
   const double d_ref = 10.0 + std::ceil(N / 256.0 / 512.0) + 1.0 + 8.0 + 2.0;
   const double d_fused = 8.0 * rows_per_cta + 5.0 + AD_WARPS + std::ceil((double)nblocks / AD_THREADS) + 5.0 + AD_WARPS + 2.0;
@@ -218,7 +217,7 @@ extern "C" int ifx_create(const ifx_input* in, const double* xf, const double* y
   s->in = *in;
   s->opt = opt;
   s->device = opt.device;
-  if (const char* e = std::getenv("IFX_KERNEL_VARIANT")) { const int v = std::atoi(e); if (v >= 1 && v <= 4) s->kernel_variant = v; }
+  if (const char* e = std::getenv("IFX_KERNEL_VARIANT")) { const int v = std::atoi(e); if (v == 1 || v == 4) s->kernel_variant = v; }
   if (const char* e = std::getenv("IFX_TUNE_AD")) s->tune_ad = std::atoi(e);
   if (const char* e = std::getenv("IFX_TUNE_PPE")) s->tune_ppe = std::atoi(e);
   if (const char* e = std::getenv("IFX_ROWS_PER_CTA")) s->rows_override = std::atoi(e);
@@ -253,8 +252,15 @@ extern "C" int ifx_create(const ifx_input* in, const double* xf, const double* y
     if ((rc = alloc_field(&s->uf)) != IFX_OK) return bail(rc);
     if ((rc = alloc_field(&s->vf)) != IFX_OK) return bail(rc);
   }
-  if (opt.compat == IFX_COMPAT_FULL)
+  if (opt.compat == IFX_COMPAT_FULL) {
     if ((rc = alloc_field(&s->rhs)) != IFX_OK) return bail(rc);
+    if (cudaMalloc(&s->d_ub, sizeof(double) * 64) != cudaSuccess || cudaMalloc(&s->d_vb, sizeof(double) * 64) != cudaSuccess) {
+      s->err = "cudaMalloc body velocities";
+      return bail(IFX_ERR_CUDA);
+    }
+    cudaMemsetAsync(s->d_ub, 0, sizeof(double) * 64, s->stream);
+    cudaMemsetAsync(s->d_vb, 0, sizeof(double) * 64, s->stream);
+  }
   if (cudaMalloc(&s->celltype, s->field_elems) != cudaSuccess) { s->err = "cudaMalloc celltype"; return bail(IFX_ERR_CUDA); }
   launch_fill_u8(s->celltype, s->field_elems, IFX_FLUID, s->stream);
   s->launches++;
@@ -277,10 +283,10 @@ extern "C" int ifx_destroy(ifx_solver* s) {
   if (s->stream) cudaStreamSynchronize(s->stream);
   double* fields[] = {s->u[0], s->u[1], s->v[0], s->v[1], s->p[0], s->p[1], s->sx, s->sy, s->rhs, s->uf, s->vf,
                       s->partials, s->res_a, s->res_b, s->red_partial, s->red_out, s->d_xm, s->d_ym, s->d_ub, s->d_vb,
-                      s->gc.w_dir, s->gc.w_neu, s->gc.bi, s->gc.ip};
+                      s->d_bbox, s->gc.w_dir, s->gc.w_neu, s->gc.bi, s->gc.ip, s->gc_tmp_a, s->gc_tmp_b};
   for (double* f : fields) if (f) cudaFree(f);
   int* ifields[] = {s->d_body_off, s->gc.cell, s->gc.ref_id, s->gc.stencil, s->gc.stencil_ref, s->gc.body,
-                    s->d_counters, s->d_rowcount};
+                    s->d_counters, s->d_rowcount, s->d_rowstart};
   for (int* f : ifields) if (f) cudaFree(f);
   for (double* t : s->tables) cudaFree(t);
   if (s->celltype) cudaFree(s->celltype);
@@ -329,6 +335,10 @@ extern "C" int ifx_initialize(ifx_solver* s) {
     IFX_CUDA(s, cudaMemsetAsync(s->vf, 0, sizeof(double) * s->field_elems, s->stream));
   }
   s->faces_valid = false;
+  s->state_bc_fresh = false;
+  s->bodies_dirty = s->nbodies > 0;      // the cell types were just reset to all-fluid
+  s->has_gc = false;
+  s->gc.count = 0;
   s->initialized = true;
   IFX_CUDA(s, cudaStreamSynchronize(s->stream));
   return IFX_OK;
@@ -387,7 +397,7 @@ extern "C" int ifx_set_field(ifx_solver* s, ifx_field f, const double* host, siz
     double* other = (f == IFX_FIELD_U) ? s->u[s->cur_uv ^ 1] : (f == IFX_FIELD_V) ? s->v[s->cur_uv ^ 1] : s->p[s->cur_p ^ 1];
     s->launches++;
     IFX_CUDA(s, launch_copy_ring(L, v.dev, other, nullptr, nullptr, s->stream));
-    if (f != IFX_FIELD_P) s->faces_valid = false;
+    if (f != IFX_FIELD_P) { s->faces_valid = false; s->state_bc_fresh = false; }
   }
   if (f == IFX_FIELD_UF || f == IFX_FIELD_VF) s->faces_valid = true;
   IFX_CUDA(s, cudaStreamSynchronize(s->stream));
@@ -459,33 +469,29 @@ extern "C" int ifx_reduce_sum(ifx_solver* s, const double* host, size_t n, doubl
 static int launch_ad_jacobi(ifx_solver* s, AdJacobiArgs& a, dim3 grid, bool write_res) {
   s->launches++;
   if (s->kernel_variant == 1) IFX_CUDA(s, ifx::launch_ad_jacobi(a, grid, s->stream, write_res, s->has_gc));
-  else if (s->kernel_variant == 2) IFX_CUDA(s, ifx::launch_ad_jacobi_v2(a, grid, s->stream, write_res, s->has_gc, s->tune_ad));
-  else if (s->kernel_variant == 3) IFX_CUDA(s, ifx::launch_ad_jacobi_v3(a, grid, s->stream, write_res, s->has_gc, s->tune_ad));
   else IFX_CUDA(s, ifx::launch_ad_jacobi_v4(a, grid, s->stream, write_res, s->tune_ad));
   return IFX_OK;
 }
 
 // reference-order evaluation of the two residual arrays + stop decision (ADSolver.cu:360-366, :315)
-static int exact_decide(ifx_solver* s, const ReduceCfg& rc, bool two_arrays) {
+int ifx::exact_decide(ifx_solver* s, const ReduceCfg& rc, bool two_arrays) {
   const size_t N = (size_t)s->L.nx * s->L.ny;
   int r = reduce_reference_order(s, s->res_a, N, s->red_out);
   if (r != IFX_OK) return r;
   if (two_arrays) {
     if ((r = reduce_reference_order(s, s->res_b, N, s->red_out + 1)) != IFX_OK) return r;
   } else {
-    IFX_CUDA(s, cudaMemsetAsync(s->red_out + 1, 0, sizeof(double), s->stream));
+    // Poisson: second sum = sum |r| of the same array, same summation order
+    if ((r = reduce_reference_order(s, s->res_a, N, s->red_out + 1, true)) != IFX_OK) return r;
   }
   s->launches++;
   IFX_CUDA(s, launch_decide_exact(s->ctl, s->red_out, rc, s->stream));
   return IFX_OK;
 }
 
-extern "C" int ifx_ad_solve(ifx_solver* s, ifx_step_stats* st) {
-  if (!s) return IFX_ERR_INVALID;
-  IFX_CUDA(s, cudaSetDevice(s->device));
+int ifx::run_ad_loop(ifx_solver* s, ifx_step_stats* st, bool full) {
   const Layout& L = s->L;
   const bool exact = s->opt.reduce_mode == IFX_REDUCE_REFERENCE;
-  const bool full = s->opt.compat == IFX_COMPAT_FULL;
   const int itermax = s->in.AD_itermax;
   const int ry = rows_per_cta_for(s, 2);
   const dim3 grid = tile_grid(s, ry, 2);
@@ -508,7 +514,6 @@ extern "C" int ifx_ad_solve(ifx_solver* s, ifx_step_stats* st) {
   fill_bc(s, sa.two_bc_u, sa.two_bc_v);
   sa.rows_per_cta = ry;
   if (full) {
-    if (!s->faces_valid) return fail(s, IFX_ERR_STATE, "face velocities not initialised (call ifx_step / ifx_iblank_update)");
     IFX_CUDA(s, launch_ad_source(sa, grid_src, s->stream, SRC_FACES));
   } else if (L.nx <= L.ny) {
     IFX_CUDA(s, launch_ad_source(sa, grid_src, s->stream, SRC_REF_VF_ZERO));     // vf == 0 (App. A Q2)
@@ -521,6 +526,7 @@ extern "C" int ifx_ad_solve(ifx_solver* s, ifx_step_stats* st) {
   IFX_CUDA(s, cudaMemsetAsync(s->ctl, 0, sizeof(LoopCtl), s->stream));
   if (itermax <= 0) {   // while-condition false on entry: zero iterations (ADSolver.cu:315)
     if (st) { st->ad_iters = 0; st->ad_ures = 1.0; st->ad_vres = 1.0; }
+    IFX_CUDA(s, cudaStreamSynchronize(s->stream));
     return IFX_OK;
   }
 
@@ -551,6 +557,11 @@ extern "C" int ifx_ad_solve(ifx_solver* s, ifx_step_stats* st) {
       set_iter(++m);
       ja.force = 0;
       if ((rc = launch_ad_jacobi(s, ja, grid, exact)) != IFX_OK) return rc;
+      if (full && s->has_gc) {   // ghost cells of iterate m from iterate m-1 (Jacobi-lagged, like every other cell)
+        s->launches++;
+        IFX_CUDA(s, launch_gc_velocity(s->gc.count, s->gc.cell, s->gc.stencil, s->gc.w_dir, s->gc.body, s->d_ub, s->d_vb,
+                                       ja.uC, ja.vC, ja.uT, ja.vT, 0, s->ctl, m, s->stream));
+      }
       if (exact && (rc = exact_decide(s, ja.rc, true)) != IFX_OK) return rc;
     }
     if ((rc = fetch_ctl(s)) != IFX_OK) return rc;
@@ -575,7 +586,7 @@ extern "C" int ifx_ad_solve(ifx_solver* s, ifx_step_stats* st) {
   const int K = s->h_ctl->iter;
   s->cur_uv = (base + K) & 1;
   s->last_ad_iters = K;
-  if (K == 1) {   // final buffer's ghost ring was never written this step: give it BC(start field)
+  if (K == 1 && !full) {   // final buffer's ghost ring was never written this step: give it BC(start field)
     s->launches++;
     IFX_CUDA(s, launch_copy_ring(L, s->u[base], s->u[s->cur_uv], s->v[base], s->v[s->cur_uv], s->stream));
   }
@@ -597,18 +608,13 @@ extern "C" int ifx_ad_solve(ifx_solver* s, ifx_step_stats* st) {
 static int launch_ppe_sweep(ifx_solver* s, PpeSweepArgs& a, dim3 grid, bool laplace_ref, bool write_res) {
   s->launches++;
   if (s->kernel_variant == 1) IFX_CUDA(s, ifx::launch_ppe_sweep(a, grid, s->stream, laplace_ref, write_res, s->has_gc));
-  else if (s->kernel_variant == 2) IFX_CUDA(s, ifx::launch_ppe_sweep_v2(a, grid, s->stream, laplace_ref, write_res, s->has_gc, s->tune_ppe));
-  else if (s->kernel_variant == 3) IFX_CUDA(s, ifx::launch_ppe_sweep_v3(a, grid, s->stream, laplace_ref, write_res, s->has_gc, s->tune_ppe));
   else IFX_CUDA(s, ifx::launch_ppe_sweep_v4(a, grid, s->stream, laplace_ref, write_res, s->tune_ppe));
   return IFX_OK;
 }
 
-extern "C" int ifx_ppe_solve(ifx_solver* s, ifx_step_stats* st) {
-  if (!s) return IFX_ERR_INVALID;
-  IFX_CUDA(s, cudaSetDevice(s->device));
+int ifx::run_ppe_loop(ifx_solver* s, ifx_step_stats* st, bool laplace_ref) {
   const Layout& L = s->L;
   const bool exact = s->opt.reduce_mode == IFX_REDUCE_REFERENCE;
-  const bool laplace_ref = s->opt.compat == IFX_COMPAT_REFERENCE;
   const int itermax = s->in.PPE_itermax;
   const int ry = rows_per_cta_for(s, 0);
   const dim3 grid = tile_grid(s, ry, 0);
@@ -686,31 +692,3 @@ extern "C" int ifx_ppe_solve(ifx_solver* s, ifx_step_stats* st) {
   return IFX_OK;
 }
 
-extern "C" int ifx_correct(ifx_solver* s, ifx_step_stats* st) {
-  (void)st;
-  if (!s) return IFX_ERR_INVALID;
-  return fail(s, IFX_ERR_INVALID, "ifx_correct requires IFX_COMPAT_FULL (the reference has no projection, AD_PPE_Correction.cu:1-12)");
-}
-
-// one iteration of main()'s time loop (main.cu:93-96)
-extern "C" int ifx_step(ifx_solver* s, ifx_step_stats* st) {
-  if (!s) return IFX_ERR_INVALID;
-  if (st) std::memset(st, 0, sizeof(*st));
-  if (s->opt.compat == IFX_COMPAT_REFERENCE) {
-    int rc = ifx_ad_solve(s, st);
-    if (rc == IFX_OK && st) st->ms_total = st->ms_ad;
-    return rc;
-  }
-  return fail(s, IFX_ERR_INVALID, "IFX_COMPAT_FULL step not built yet");
-}
-
-extern "C" int ifx_set_bodies(ifx_solver* s, int, const int*, const double*, const double*, const double*, const double*) {
-  return fail(s, IFX_ERR_INVALID, "immersed bodies not built yet");
-}
-extern "C" int ifx_iblank_update(ifx_solver* s, ifx_step_stats*) { return fail(s, IFX_ERR_INVALID, "immersed bodies not built yet"); }
-extern "C" int ifx_ghost_cell_count(const ifx_solver* s) { return s ? s->gc.count : 0; }
-extern "C" int ifx_get_ghost_cells(ifx_solver* s, int*, int*, double*, double*, double*, int) {
-  return fail(s, IFX_ERR_INVALID, "immersed bodies not built yet");
-}
-extern "C" int ifx_ipc_export(ifx_solver* s, unsigned char*) { return fail(s, IFX_ERR_INVALID, "multi-GPU not built yet"); }
-extern "C" int ifx_ipc_connect(ifx_solver* s, const unsigned char*, int) { return fail(s, IFX_ERR_INVALID, "multi-GPU not built yet"); }

@@ -1,0 +1,288 @@
+// capi_full.cu — C-ABI entry points of the stages the reference lacks (IFX_COMPAT_FULL) and the dispatch of
+// ifx_ad_solve / ifx_ppe_solve / ifx_step between the two compat modes.
+#include "solver.h"
+
+#include <algorithm>
+#include <cstring>
+
+using namespace ifx;
+
+// ------------------------------------------------------------------------------------------------
+// boundary-condition refresh of a velocity / pressure buffer pair: ghost ring + ghost cells, the ghost cells
+// gathered from the field before any of them is overwritten (oracle: apply_velocity_bc / apply_pressure_bc)
+// ------------------------------------------------------------------------------------------------
+int ifx::full_refresh_velocity_bc(ifx_solver* s, int buf) {
+  double tu[4], tv[4];
+  fill_bc(s, tu, tv);
+  s->launches += 2;
+  IFX_CUDA(s, launch_apply_ring(s->L, s->u[buf], tu, 0, s->stream));
+  IFX_CUDA(s, launch_apply_ring(s->L, s->v[buf], tv, 0, s->stream));
+  if (s->has_gc) {
+    s->launches += 2;
+    IFX_CUDA(s, launch_gc_velocity(s->gc.count, s->gc.cell, s->gc.stencil, s->gc.w_dir, s->gc.body, s->d_ub, s->d_vb,
+                                   s->u[buf], s->v[buf], s->gc_tmp_a, s->gc_tmp_b, 1, nullptr, 0, s->stream));
+    IFX_CUDA(s, launch_gc_scatter(s->gc.count, s->gc.cell, s->gc_tmp_a, s->u[buf], s->gc_tmp_b, s->v[buf], s->stream));
+  }
+  return IFX_OK;
+}
+
+int ifx::full_refresh_pressure_bc(ifx_solver* s, int buf) {
+  s->launches++;
+  IFX_CUDA(s, launch_apply_ring(s->L, s->p[buf], nullptr, 1, s->stream));
+  if (s->has_gc) {   // diagnostic only: the solver never reads p at ghost cells (closed-face rule)
+    s->launches += 2;
+    IFX_CUDA(s, launch_gc_pressure(s->gc.count, s->gc.cell, s->gc.stencil, s->gc.w_neu, s->p[buf], s->gc_tmp_a, 1, s->stream));
+    IFX_CUDA(s, launch_gc_scatter(s->gc.count, s->gc.cell, s->gc_tmp_a, s->p[buf], nullptr, nullptr, s->stream));
+  }
+  return IFX_OK;
+}
+
+static int require_full(ifx_solver* s, const char* what) {
+  if (s->opt.compat != IFX_COMPAT_FULL)
+    return fail(s, IFX_ERR_INVALID, std::string(what) + " requires IFX_COMPAT_FULL (the reference has no such stage)");
+  if (s->kernel_variant != 4) return fail(s, IFX_ERR_INVALID, "IFX_COMPAT_FULL needs the default kernel variant");
+  return IFX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// immersed bodies
+// ------------------------------------------------------------------------------------------------
+extern "C" int ifx_set_bodies(ifx_solver* s, int nbodies, const int* offsets, const double* xm, const double* ym,
+                              const double* ubody, const double* vbody) {
+  if (!s) return IFX_ERR_INVALID;
+  int rc = require_full(s, "ifx_set_bodies");
+  if (rc != IFX_OK) return rc;
+  if (nbodies < 0 || nbodies > 63) return fail(s, IFX_ERR_INVALID, "at most 63 bodies (6-bit owner field in the cell type)");
+  if (nbodies > 0 && (!offsets || !xm || !ym)) return fail(s, IFX_ERR_INVALID, "null body arrays");
+  IFX_CUDA(s, cudaSetDevice(s->device));
+  const int nm = nbodies ? offsets[nbodies] : 0;
+  for (int b = 0; b < nbodies; b++)
+    if (offsets[b + 1] - offsets[b] < 3) return fail(s, IFX_ERR_INVALID, "a body needs at least 3 markers");
+  s->nbodies = nbodies;
+  s->h_body_off.assign(offsets, offsets + nbodies + 1);
+  if (nbodies == 0) s->h_body_off.assign(1, 0);
+  s->h_xm.assign(xm, xm + nm);
+  s->h_ym.assign(ym, ym + nm);
+  s->h_ub.assign(64, 0.0);
+  s->h_vb.assign(64, 0.0);
+  for (int b = 0; b < nbodies; b++) {
+    if (ubody) s->h_ub[b] = ubody[b];
+    if (vbody) s->h_vb[b] = vbody[b];
+  }
+  s->h_bbox.assign(4 * std::max(nbodies, 1), 0.0);
+  for (int b = 0; b < nbodies; b++) {
+    double x0 = xm[offsets[b]], x1 = x0, y0 = ym[offsets[b]], y1 = y0;
+    for (int k = offsets[b]; k < offsets[b + 1]; k++) {
+      x0 = std::min(x0, xm[k]); x1 = std::max(x1, xm[k]);
+      y0 = std::min(y0, ym[k]); y1 = std::max(y1, ym[k]);
+    }
+    s->h_bbox[4 * b] = x0; s->h_bbox[4 * b + 1] = x1; s->h_bbox[4 * b + 2] = y0; s->h_bbox[4 * b + 3] = y1;
+  }
+  if ((size_t)nm + 1 > s->markers_cap) {
+    if (s->d_xm) cudaFree(s->d_xm);
+    if (s->d_ym) cudaFree(s->d_ym);
+    s->d_xm = s->d_ym = nullptr;
+    s->markers_cap = (size_t)nm + 1024;
+    IFX_CUDA(s, cudaMalloc(&s->d_xm, sizeof(double) * s->markers_cap));
+    IFX_CUDA(s, cudaMalloc(&s->d_ym, sizeof(double) * s->markers_cap));
+  }
+  if (!s->d_body_off) IFX_CUDA(s, cudaMalloc(&s->d_body_off, sizeof(int) * 65));
+  if (!s->d_bbox) IFX_CUDA(s, cudaMalloc(&s->d_bbox, sizeof(double) * 4 * 64));
+  IFX_CUDA(s, cudaMemcpyAsync(s->d_body_off, s->h_body_off.data(), sizeof(int) * s->h_body_off.size(), cudaMemcpyHostToDevice, s->stream));
+  if (nm) {
+    IFX_CUDA(s, cudaMemcpyAsync(s->d_xm, s->h_xm.data(), sizeof(double) * nm, cudaMemcpyHostToDevice, s->stream));
+    IFX_CUDA(s, cudaMemcpyAsync(s->d_ym, s->h_ym.data(), sizeof(double) * nm, cudaMemcpyHostToDevice, s->stream));
+  }
+  IFX_CUDA(s, cudaMemcpyAsync(s->d_bbox, s->h_bbox.data(), sizeof(double) * s->h_bbox.size(), cudaMemcpyHostToDevice, s->stream));
+  IFX_CUDA(s, cudaMemcpyAsync(s->d_ub, s->h_ub.data(), sizeof(double) * 64, cudaMemcpyHostToDevice, s->stream));
+  IFX_CUDA(s, cudaMemcpyAsync(s->d_vb, s->h_vb.data(), sizeof(double) * 64, cudaMemcpyHostToDevice, s->stream));
+  IFX_CUDA(s, cudaStreamSynchronize(s->stream));      // host vectors may be reassigned by the next call
+  s->bodies_dirty = true;
+  return IFX_OK;
+}
+
+static int ensure_gc_capacity(ifx_solver* s, int n) {
+  GhostCells& g = s->gc;
+  if (n <= g.capacity) return IFX_OK;
+  int* ip[] = {g.cell, g.ref_id, g.stencil, g.stencil_ref, g.body};
+  for (int* p : ip) if (p) cudaFree(p);
+  double* dp[] = {g.w_dir, g.w_neu, g.bi, g.ip, s->gc_tmp_a, s->gc_tmp_b};
+  for (double* p : dp) if (p) cudaFree(p);
+  const int cap = n + n / 4 + 1024;
+  g = GhostCells();
+  s->gc_tmp_a = s->gc_tmp_b = nullptr;
+  IFX_CUDA(s, cudaMalloc(&g.cell, sizeof(int) * cap));
+  IFX_CUDA(s, cudaMalloc(&g.ref_id, sizeof(int) * cap));
+  IFX_CUDA(s, cudaMalloc(&g.body, sizeof(int) * cap));
+  IFX_CUDA(s, cudaMalloc(&g.stencil, sizeof(int) * 4 * cap));
+  IFX_CUDA(s, cudaMalloc(&g.stencil_ref, sizeof(int) * 4 * cap));
+  IFX_CUDA(s, cudaMalloc(&g.w_dir, sizeof(double) * 5 * cap));
+  IFX_CUDA(s, cudaMalloc(&g.w_neu, sizeof(double) * 4 * cap));
+  IFX_CUDA(s, cudaMalloc(&g.bi, sizeof(double) * 2 * cap));
+  IFX_CUDA(s, cudaMalloc(&g.ip, sizeof(double) * 2 * cap));
+  IFX_CUDA(s, cudaMalloc(&s->gc_tmp_a, sizeof(double) * cap));
+  IFX_CUDA(s, cudaMalloc(&s->gc_tmp_b, sizeof(double) * cap));
+  g.capacity = cap;
+  return IFX_OK;
+}
+
+// replaces iBlankComputeKernel (preSim.cu:110-136) + the ghost-cell machinery the reference lacks
+extern "C" int ifx_iblank_update(ifx_solver* s, ifx_step_stats* st) {
+  if (!s) return IFX_ERR_INVALID;
+  int rc = require_full(s, "ifx_iblank_update");
+  if (rc != IFX_OK) return rc;
+  IFX_CUDA(s, cudaSetDevice(s->device));
+  const Layout& L = s->L;
+  IFX_CUDA(s, cudaEventRecord(s->ev[6], s->stream));
+  if (!s->d_rowcount) {
+    IFX_CUDA(s, cudaMalloc(&s->d_rowcount, sizeof(int) * (L.nyl + 1)));
+    IFX_CUDA(s, cudaMalloc(&s->d_rowstart, sizeof(int) * (L.nyl + 2)));
+    IFX_CUDA(s, cudaMalloc(&s->d_counters, sizeof(int) * 4));
+  }
+  if (!s->d_body_off) {   // no bodies were ever set: everything is fluid
+    int zero[65] = {0};
+    IFX_CUDA(s, cudaMalloc(&s->d_body_off, sizeof(int) * 65));
+    IFX_CUDA(s, cudaMalloc(&s->d_bbox, sizeof(double) * 4 * 64));
+    IFX_CUDA(s, cudaMemcpy(s->d_body_off, zero, sizeof(zero), cudaMemcpyHostToDevice));
+  }
+  s->launches += 4;
+  IFX_CUDA(s, launch_classify(L, s->M.xc, s->M.yc, s->nbodies, s->d_body_off, s->d_xm, s->d_ym, s->d_bbox, s->celltype, s->stream));
+  IFX_CUDA(s, launch_gc_count(L, s->celltype, s->d_rowcount, s->d_rowstart, s->d_counters, s->stream));
+  int total = 0;
+  IFX_CUDA(s, cudaMemcpyAsync(&total, s->d_counters, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+  IFX_CUDA(s, cudaStreamSynchronize(s->stream));
+  if ((rc = ensure_gc_capacity(s, total)) != IFX_OK) return rc;
+  s->gc.count = total;
+  s->has_gc = total > 0;
+  if (total > 0) {
+    s->launches += 2;
+    IFX_CUDA(s, launch_gc_build(L, s->M.xc, s->M.yc, s->d_body_off, s->d_xm, s->d_ym, s->celltype, s->d_rowstart, total,
+                                s->gc.cell, s->gc.ref_id, s->gc.body, s->gc.stencil, s->gc.stencil_ref, s->gc.w_dir,
+                                s->gc.w_neu, s->gc.bi, s->gc.ip, s->stream));
+  }
+  s->bodies_dirty = false;
+  s->faces_valid = false;          // closed faces moved with the bodies
+  s->state_bc_fresh = false;
+  IFX_CUDA(s, cudaEventRecord(s->ev[7], s->stream));
+  IFX_CUDA(s, cudaEventSynchronize(s->ev[7]));
+  if (st) cudaEventElapsedTime(&st->ms_ib, s->ev[6], s->ev[7]);
+  return IFX_OK;
+}
+
+extern "C" int ifx_ghost_cell_count(const ifx_solver* s) { return s ? s->gc.count : 0; }
+
+// weights: 10 doubles per ghost cell = {wd0..wd3, cd, wn0..wn3, body}
+extern "C" int ifx_get_ghost_cells(ifx_solver* s, int* cell_id, int* stencil_id, double* weights, double* bi_xy,
+                                   double* ip_xy, int capacity) {
+  if (!s) return IFX_ERR_INVALID;
+  IFX_CUDA(s, cudaSetDevice(s->device));
+  const int n = s->gc.count;
+  if (capacity < n) return fail(s, IFX_ERR_INVALID, "capacity too small");
+  if (n == 0) return IFX_OK;
+  IFX_CUDA(s, cudaStreamSynchronize(s->stream));
+  if (cell_id) IFX_CUDA(s, cudaMemcpy(cell_id, s->gc.ref_id, sizeof(int) * n, cudaMemcpyDeviceToHost));
+  if (stencil_id) IFX_CUDA(s, cudaMemcpy(stencil_id, s->gc.stencil_ref, sizeof(int) * 4 * n, cudaMemcpyDeviceToHost));
+  if (bi_xy) IFX_CUDA(s, cudaMemcpy(bi_xy, s->gc.bi, sizeof(double) * 2 * n, cudaMemcpyDeviceToHost));
+  if (ip_xy) IFX_CUDA(s, cudaMemcpy(ip_xy, s->gc.ip, sizeof(double) * 2 * n, cudaMemcpyDeviceToHost));
+  if (weights) {
+    std::vector<double> wd(5 * (size_t)n), wn(4 * (size_t)n);
+    std::vector<int> body(n);
+    IFX_CUDA(s, cudaMemcpy(wd.data(), s->gc.w_dir, sizeof(double) * 5 * n, cudaMemcpyDeviceToHost));
+    IFX_CUDA(s, cudaMemcpy(wn.data(), s->gc.w_neu, sizeof(double) * 4 * n, cudaMemcpyDeviceToHost));
+    IFX_CUDA(s, cudaMemcpy(body.data(), s->gc.body, sizeof(int) * n, cudaMemcpyDeviceToHost));
+    for (int g = 0; g < n; g++) {
+      std::memcpy(weights + 10 * (size_t)g, wd.data() + 5 * (size_t)g, 5 * sizeof(double));
+      std::memcpy(weights + 10 * (size_t)g + 5, wn.data() + 4 * (size_t)g, 4 * sizeof(double));
+      weights[10 * (size_t)g + 9] = body[g];
+    }
+  }
+  return IFX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// stage entry points
+// ------------------------------------------------------------------------------------------------
+static int full_prepare(ifx_solver* s) {
+  int rc;
+  if (s->bodies_dirty && (rc = ifx_iblank_update(s, nullptr)) != IFX_OK) return rc;
+  return IFX_OK;
+}
+
+// replaces ImmerseFlow::ADsolver(), ADSolver.cu:268-395
+extern "C" int ifx_ad_solve(ifx_solver* s, ifx_step_stats* st) {
+  if (!s) return IFX_ERR_INVALID;
+  IFX_CUDA(s, cudaSetDevice(s->device));
+  if (s->opt.compat == IFX_COMPAT_REFERENCE) return run_ad_loop(s, st, false);
+  int rc = require_full(s, "predictor");
+  if (rc != IFX_OK) return rc;
+  if ((rc = full_prepare(s)) != IFX_OK) return rc;
+  // start-of-step consistency: ring + ghost cells of (u, v); first step: face velocities from the cells
+  if ((rc = full_refresh_velocity_bc(s, s->cur_uv)) != IFX_OK) return rc;
+  if (!s->faces_valid) {
+    s->launches++;
+    IFX_CUDA(s, launch_faces_init(s->L, s->M, s->celltype, s->d_ub, s->d_vb, s->u[s->cur_uv], s->v[s->cur_uv], s->uf, s->vf,
+                                  s->stream));
+    s->faces_valid = true;
+  }
+  if ((rc = run_ad_loop(s, st, true)) != IFX_OK) return rc;
+  if ((rc = full_refresh_velocity_bc(s, s->cur_uv)) != IFX_OK) return rc;
+  IFX_CUDA(s, cudaStreamSynchronize(s->stream));
+  return IFX_OK;
+}
+
+// replaces ImmerseFlow::PPESolver(), PPESolver.cu:137-205
+extern "C" int ifx_ppe_solve(ifx_solver* s, ifx_step_stats* st) {
+  if (!s) return IFX_ERR_INVALID;
+  IFX_CUDA(s, cudaSetDevice(s->device));
+  if (s->opt.compat == IFX_COMPAT_REFERENCE) return run_ppe_loop(s, st, true);
+  int rc = require_full(s, "Poisson solve");
+  if (rc != IFX_OK) return rc;
+  if ((rc = full_prepare(s)) != IFX_OK) return rc;
+  // a15: source term from the predicted velocities (their ring and ghost cells were refreshed by the predictor)
+  s->launches++;
+  IFX_CUDA(s, launch_ppe_rhs(s->L, s->M, s->celltype, s->d_ub, s->d_vb, s->u[s->cur_uv], s->v[s->cur_uv], s->rhs, s->stream));
+  if ((rc = run_ppe_loop(s, st, false)) != IFX_OK) return rc;
+  if ((rc = full_refresh_pressure_bc(s, s->cur_p)) != IFX_OK) return rc;
+  IFX_CUDA(s, cudaStreamSynchronize(s->stream));
+  return IFX_OK;
+}
+
+// the projection the reference leaves empty, AD_PPE_Correction.cu:1-12
+extern "C" int ifx_correct(ifx_solver* s, ifx_step_stats* st) {
+  if (!s) return IFX_ERR_INVALID;
+  int rc = require_full(s, "ifx_correct");
+  if (rc != IFX_OK) return rc;
+  IFX_CUDA(s, cudaSetDevice(s->device));
+  if ((rc = full_prepare(s)) != IFX_OK) return rc;
+  IFX_CUDA(s, cudaEventRecord(s->ev[4], s->stream));
+  const int cur = s->cur_uv;
+  s->launches++;
+  IFX_CUDA(s, launch_correct(s->L, s->M, s->celltype, s->d_ub, s->d_vb, s->u[cur], s->v[cur], s->p[s->cur_p], s->u[cur ^ 1],
+                             s->v[cur ^ 1], s->uf, s->vf, s->stream));
+  s->cur_uv = cur ^ 1;
+  s->faces_valid = true;
+  if ((rc = full_refresh_velocity_bc(s, s->cur_uv)) != IFX_OK) return rc;
+  IFX_CUDA(s, cudaEventRecord(s->ev[5], s->stream));
+  IFX_CUDA(s, cudaEventSynchronize(s->ev[5]));
+  if (st) cudaEventElapsedTime(&st->ms_correct, s->ev[4], s->ev[5]);
+  return IFX_OK;
+}
+
+// one iteration of main()'s time loop (main.cu:93-96)
+extern "C" int ifx_step(ifx_solver* s, ifx_step_stats* st) {
+  if (!s) return IFX_ERR_INVALID;
+  ifx_step_stats local;
+  if (!st) st = &local;
+  std::memset(st, 0, sizeof(*st));
+  int rc = ifx_ad_solve(s, st);
+  if (rc != IFX_OK) return rc;
+  if (s->opt.compat == IFX_COMPAT_FULL) {
+    if ((rc = ifx_ppe_solve(s, st)) != IFX_OK) return rc;
+    if ((rc = ifx_correct(s, st)) != IFX_OK) return rc;
+  }
+  st->ms_total = st->ms_ad + st->ms_ppe + st->ms_correct + st->ms_ib;
+  return IFX_OK;
+}
+
+extern "C" int ifx_ipc_export(ifx_solver* s, unsigned char*) { return fail(s, IFX_ERR_INVALID, "multi-GPU not built yet"); }
+extern "C" int ifx_ipc_connect(ifx_solver* s, const unsigned char*, int) { return fail(s, IFX_ERR_INVALID, "multi-GPU not built yet"); }

@@ -142,21 +142,38 @@ cudaError_t launch_copy_ring(const Layout& L, const double* s0, double* d0, cons
 cudaError_t launch_ppe_sweep(const PpeSweepArgs& a, dim3 grid, cudaStream_t st, bool laplace_ref, bool write_res,
                              bool has_gc);
 cudaError_t launch_set_pressure_bc_ref(const Layout& L, double* p0, double* p1, cudaStream_t st);
-// kernels_v2.cu — the same sweeps behind a cp.async.bulk + mbarrier row pipeline (default variant)
-cudaError_t launch_ad_jacobi_v2(const AdJacobiArgs& a, dim3 grid, cudaStream_t st, bool write_res, bool has_gc, int tune);
-cudaError_t launch_ppe_sweep_v2(const PpeSweepArgs& a, dim3 grid, cudaStream_t st, bool laplace_ref, bool write_res,
-                                bool has_gc, int tune);
-// kernels_v3.cu — pipeline + rows read from the smem ring, 4-8 columns per thread, predictor split by field (default)
-cudaError_t launch_ad_jacobi_v3(const AdJacobiArgs& a, dim3 grid, cudaStream_t st, bool write_res, bool has_gc, int tune);
-cudaError_t launch_ppe_sweep_v3(const PpeSweepArgs& a, dim3 grid, cudaStream_t st, bool laplace_ref, bool write_res,
-                                bool has_gc, int tune);
-int v3_tile_cols(int mode /*0,1: Poisson, 2: predictor*/, int tune);
 // kernels_v4.cu — v3 + lean interior path, in-line shared-reciprocal division, smem row tables (default)
 cudaError_t launch_ad_jacobi_v4(const AdJacobiArgs& a, dim3 grid, cudaStream_t st, bool write_res, int tune);
 cudaError_t launch_ppe_sweep_v4(const PpeSweepArgs& a, dim3 grid, cudaStream_t st, bool laplace_ref, bool write_res, int tune);
 int v4_tile_cols(int mode /*0,1: Poisson, 2: predictor*/, int tune);
+// kernels_full.cu — PPE source term, projection, BC refresh (IFX_COMPAT_FULL)
+cudaError_t launch_apply_ring(const Layout& L, double* q, const double* two_bc, int neumann, cudaStream_t st);
+cudaError_t launch_faces_init(const Layout& L, const Metrics& M, const uint8_t* ct, const double* ub, const double* vb,
+                              const double* u, const double* v, double* uf, double* vf, cudaStream_t st);
+cudaError_t launch_ppe_rhs(const Layout& L, const Metrics& M, const uint8_t* ct, const double* ub, const double* vb,
+                           const double* u, const double* v, double* rhs, cudaStream_t st);
+cudaError_t launch_correct(const Layout& L, const Metrics& M, const uint8_t* ct, const double* ub, const double* vb,
+                           const double* us, const double* vs, const double* p, double* un, double* vn, double* uf,
+                           double* vf, cudaStream_t st);
+// kernels_ib.cu — classification, ghost-cell list and stencils, ghost-cell values
+cudaError_t launch_classify(const Layout& L, const double* xc, const double* yc, int nbodies, const int* off,
+                            const double* xm, const double* ym, const double* bbox, uint8_t* celltype, cudaStream_t st);
+cudaError_t launch_gc_count(const Layout& L, const uint8_t* celltype, int* rowcount, int* rowstart, int* total,
+                            cudaStream_t st);
+cudaError_t launch_gc_build(const Layout& L, const double* xc, const double* yc, const int* off, const double* xm,
+                            const double* ym, const uint8_t* celltype, const int* rowstart, int ngc, int* cell, int* ref_id,
+                            int* body, int* stencil, int* stencil_ref, double* wd, double* wn, double* bi, double* ip,
+                            cudaStream_t st);
+cudaError_t launch_gc_velocity(int ngc, const int* cell, const int* stencil, const double* wd, const int* body,
+                               const double* ub, const double* vb, const double* usrc, const double* vsrc, double* udst,
+                               double* vdst, int gather, const LoopCtl* ctl, int iter, cudaStream_t st);
+cudaError_t launch_gc_pressure(int ngc, const int* cell, const int* stencil, const double* wn, const double* psrc,
+                               double* pdst, int gather, cudaStream_t st);
+cudaError_t launch_gc_scatter(int ngc, const int* cell, const double* a, double* qa, const double* b, double* qb,
+                              cudaStream_t st);
 // kernels_reduce.cu — the reference's summation order (preSim.cu:12-50, 376-441)
-cudaError_t launch_reduce6(const double* in, size_t n, double* partial, double* out, cudaStream_t st);
+cudaError_t launch_reduce6(const double* in, size_t n, double* partial, double* out, cudaStream_t st,
+                           bool abs_values = false);
 cudaError_t launch_decide_exact(LoopCtl* ctl, const double* sums, const ReduceCfg& rc, cudaStream_t st);
 // kernels_misc.cu / kernels_ic.cu
 cudaError_t launch_init_vortex(const Layout& L, const double* xc, const double* yc, double* u, double* v, double* p,

@@ -23,14 +23,14 @@ static __global__ void k_unpack(Layout L, const double* __restrict__ dense, doub
   const int j = j_lo + blockIdx.y;
   if (i < L.nx && j < j_hi) padded[lidx(L, i, j - L.j0)] = dense[(size_t)(j - j_lo) * L.nx + i];
 }
-// cell types -> doubles.  raw = 0: the reference's iBlank (1.0 fluid, 0.0 otherwise); raw = 1: type code.
+// cell types -> doubles.  raw = 0: the reference's iBlank (1.0 fluid, 0.0 otherwise); raw = 1: type code (low 2 bits).
 static __global__ void k_pack_u8(Layout L, const uint8_t* __restrict__ padded, double* __restrict__ dense,
                           int j_lo, int j_hi, int raw) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int j = j_lo + blockIdx.y;
   if (i < L.nx && j < j_hi) {
     const uint8_t c = padded[lidx(L, i, j - L.j0)];
-    dense[(size_t)(j - j_lo) * L.nx + i] = raw ? (double)c : (c == IFX_FLUID ? 1.0 : 0.0);
+    dense[(size_t)(j - j_lo) * L.nx + i] = raw ? (double)(c & 3) : (c == IFX_FLUID ? 1.0 : 0.0);
   }
 }
 

@@ -30,6 +30,7 @@ __device__ __forceinline__ double tree256(double s, double* sh) {
   return s;
 }
 
+template <bool ABS>
 static __global__ void __launch_bounds__(256) k_reduce6_level1(const double* __restrict__ in,
                                                         double* __restrict__ partial, unsigned n) {
   __shared__ double sh[256];
@@ -38,7 +39,9 @@ static __global__ void __launch_bounds__(256) k_reduce6_level1(const double* __r
   const unsigned i = blockIdx.x * 512u + t;
   double s = 0.0;
   if (i < n) {
-    double v = (i + 256u < n) ? in[i] + in[i + 256u] : in[i];
+    double v;
+    if (ABS) v = (i + 256u < n) ? fabs(in[i]) + fabs(in[i + 256u]) : fabs(in[i]);   // sum of |r| in the same order
+    else v = (i + 256u < n) ? in[i] + in[i + 256u] : in[i];
     s = s + v;                                       // sdata[tid] (= 0) += ...
   }
   s = tree256(s, sh);
@@ -76,9 +79,10 @@ static __global__ void k_decide_exact(LoopCtl* ctl, const double* sums, ReduceCf
 }
 
 // ImmerseFlow::Reduction (preSim.cu:376-445): B = ceil(n/256) blocks (preSim.cu:193), then one block.
-cudaError_t launch_reduce6(const double* in, size_t n, double* partial, double* out, cudaStream_t st) {
+cudaError_t launch_reduce6(const double* in, size_t n, double* partial, double* out, cudaStream_t st, bool abs_values) {
   const unsigned B = (unsigned)((n + 255) / 256);
-  k_reduce6_level1<<<B, 256, 0, st>>>(in, partial, (unsigned)n);
+  if (abs_values) k_reduce6_level1<true><<<B, 256, 0, st>>>(in, partial, (unsigned)n);
+  else k_reduce6_level1<false><<<B, 256, 0, st>>>(in, partial, (unsigned)n);
   k_reduce6_level2<<<1, 256, 0, st>>>(partial, B, out);
   return cudaGetLastError();
 }

@@ -55,14 +55,19 @@ struct ifx_solver {
   // immersed boundary
   int nbodies = 0;
   std::vector<int> h_body_off;
-  std::vector<double> h_xm, h_ym, h_ub, h_vb;
-  int *d_body_off = nullptr;
-  double *d_xm = nullptr, *d_ym = nullptr, *d_ub = nullptr, *d_vb = nullptr;
+  std::vector<double> h_xm, h_ym, h_ub, h_vb, h_bbox;
+  int* d_body_off = nullptr;
+  double *d_xm = nullptr, *d_ym = nullptr, *d_bbox = nullptr;
+  size_t markers_cap = 0;
+  double *d_ub = nullptr, *d_vb = nullptr;   // 64 entries each, always allocated in FULL mode
   bool bodies_dirty = false;
   bool has_gc = false;
   GhostCells gc;
-  int* d_counters = nullptr;
-  int* d_rowcount = nullptr;
+  int* d_counters = nullptr;         // [0] ghost-cell total
+  int* d_rowcount = nullptr;         // nyl entries
+  int* d_rowstart = nullptr;         // nyl + 1 entries
+  double *gc_tmp_a = nullptr, *gc_tmp_b = nullptr;   // gather arrays for in-place ghost-cell refresh
+  bool state_bc_fresh = false;       // ring + ghost cells of u, v consistent with the interior
 
   // multi-GPU exchange
   void* xchg = nullptr;              // this rank's exchange segment (IPC-exported)
@@ -71,9 +76,9 @@ struct ifx_solver {
   void* peer_hi = nullptr;
   std::vector<void*> peer_all;
 
-  int kernel_variant = 4;            // 1: register-rolled direct loads, 2: bulk-copy pipeline + rolling,
-                                     // 3: pipeline + smem-resident rows, field-split predictor,
-                                     // 4: 3 + lean interior path / shared-reciprocal division (IFX_KERNEL_VARIANT)
+  int kernel_variant = 4;            // 1: register-rolled direct loads (kernels_ad.cu / kernels_ppe.cu, reference mode only)
+                                     // 4: bulk-copy row pipeline, lean interior path (kernels_v4.cu, default)
+                                     // (IFX_KERNEL_VARIANT; variants 2, 3 were stepping stones, see profiles/)
   int tune_ad = 0, tune_ppe = 0;     // pipeline geometry selectors (IFX_TUNE_AD / IFX_TUNE_PPE)
   int rows_override = 0;             // IFX_ROWS_PER_CTA
   int last_ad_iters = 5;
@@ -84,6 +89,19 @@ struct ifx_solver {
 
 namespace ifx {
 int fail(ifx_solver* s, int code, const std::string& msg);
+// shared by capi.cu and capi_full.cu
+int fetch_ctl(ifx_solver* s);
+int ensure_partials(ifx_solver* s, size_t nblocks);
+int ensure_exact_buffers(ifx_solver* s);
+int exact_decide(ifx_solver* s, const ReduceCfg& rc, bool two_arrays);
+int rows_per_cta_for(const ifx_solver* s, int mode);
+dim3 tile_grid(const ifx_solver* s, int ry, int mode);
+double rounding_band(const ifx_solver* s, size_t nblocks, int rows_per_cta);
+void fill_bc(const ifx_solver* s, double* two_u, double* two_v);
+int run_ad_loop(ifx_solver* s, ifx_step_stats* st, bool full);
+int run_ppe_loop(ifx_solver* s, ifx_step_stats* st, bool laplace_ref);
+int full_refresh_velocity_bc(ifx_solver* s, int buf);
+int full_refresh_pressure_bc(ifx_solver* s, int buf);
 }
 
 #define IFX_CUDA(s, call)                                                                      \

@@ -109,6 +109,46 @@ int orc_write_results_to_file(const double* x, const double* y, const double* da
 
 int orc_num_threads(void);
 
+/* ================================================================================================
+ * UNPINNED stages (ifx_oracle_full.c): the reference has no code for them; this oracle DEFINES them.
+ * ================================================================================================ */
+void orc_iblank_classify(int nx, int ny, const double* xc, const double* yc, int nbodies, const int* off,
+                         const double* xm, const double* ym, unsigned char* celltype, int* body_of);
+int orc_ghost_cells(int nx, int ny, const double* xc, const double* yc, int nbodies, const int* off,
+                    const double* xm, const double* ym, const unsigned char* celltype, const int* body_of,
+                    int capacity, int* cell, int* stencil, double* wd, double* wn, double* bi, double* ip, int* body);
+void orc_gc_update_velocity(int ngc, const int* cell, const int* stencil, const double* wd, const int* body,
+                            const double* ub, const double* vb, const double* usrc, const double* vsrc,
+                            double* udst, double* vdst);
+void orc_gc_update_pressure(int ngc, const int* cell, const int* stencil, const double* wn, const double* psrc, double* pdst);
+void orc_set_dirichlet_ring(int nx, int ny, double* q, const double* two_bc);
+void orc_set_neumann_ring(int nx, int ny, double* q);
+void orc_faces_from_cells(int nx, int ny, const double* dx, const double* dy, const double* u, const double* v,
+                          const unsigned char* celltype, const double* ub, const double* vb, double* uf, double* vf);
+void orc_ppe_source(int nx, int ny, const double* dx, const double* dy, double dt, const unsigned char* celltype,
+                    const double* uf, const double* vf, double* rhs);
+void orc_ppe_sweep_general(int nx, int ny, const double* cP, const double* cxm, const double* cxp, const double* cym,
+                           const double* cyp, const unsigned char* celltype, const double* rhs, const double* p,
+                           double* p_new, double* residual);
+void orc_correct(int nx, int ny, const double* dx, const double* dy, double dt, const unsigned char* celltype,
+                 const double* ub, const double* vb,
+                 const double* us, const double* vs, const double* p, double* u, double* v, double* uf, double* vf);
+
+typedef struct orc_full orc_full;
+orc_full* orc_full_create(int nx, int ny, const double* xf, const double* yf, double dt, double Re, int AD_itermax,
+                          int PPE_itermax, double ad_tol, double ppe_tol, int ppe_abs, const double* bc_u, const double* bc_v);
+void orc_full_destroy(orc_full* s);
+void orc_full_set_bodies(orc_full* s, int nbodies, const int* off, const double* xm, const double* ym,
+                         const double* ub, const double* vb);
+int orc_full_update_ib(orc_full* s);
+int orc_full_predictor(orc_full* s, double* stats);
+int orc_full_poisson(orc_full* s, double* stats);
+void orc_full_correct(orc_full* s);
+void orc_full_step(orc_full* s, double* stats);
+int orc_full_get(orc_full* s, int field, double* out);
+int orc_full_set(orc_full* s, int field, const double* in);
+int orc_full_ghost_cells(orc_full* s, int* cell, int* stencil, double* w10, double* bi, double* ip);
+
 #ifdef __cplusplus
 }
 #endif

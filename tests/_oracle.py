@@ -103,3 +103,90 @@ def stretched_faces(n_cells, length, ratio=1.04, seed=None):
     f *= length / f[-1]
     # 7 significant digits like the shipped grid files, so text round-trips exactly
     return np.array([float(f"{v:.7E}") for v in f])
+
+
+# ------------------------------------------------------------------------------------------------
+# UNPINNED stages (oracle/ifx_oracle_full.c): full fractional step with immersed bodies
+# ------------------------------------------------------------------------------------------------
+FIELD = {"u": 0, "v": 1, "p": 2, "iblank": 3, "uf": 4, "vf": 5, "sx": 6, "sy": 7, "ppe_rhs": 8, "celltype": 11}
+
+
+def circle_markers(cx, cy, r, n):
+    """Counter-clockwise polygon approximating a circle; generated once on the host and handed, identically, to the
+    oracle and to the CUDA path (so libm never enters the CPU/GPU comparison)."""
+    t = 2.0 * np.pi * np.arange(n) / n
+    return np.ascontiguousarray(np.stack([cx + r * np.cos(t), cy + r * np.sin(t)], axis=1))
+
+
+def ellipse_markers(cx, cy, a, b, angle, n):
+    t = 2.0 * np.pi * np.arange(n) / n
+    x, y = a * np.cos(t), b * np.sin(t)
+    ca, sa = np.cos(angle), np.sin(angle)
+    return np.ascontiguousarray(np.stack([cx + ca * x - sa * y, cy + sa * x + ca * y], axis=1))
+
+
+class FullSolver:
+    def __init__(self, xf, yf, dt, Re, ad_itermax, ppe_itermax, ad_tol=1e-6, ppe_tol=1e-6, ppe_abs=1,
+                 bc_u=(1.0, 1.0, 1.0, 1.0), bc_v=(0.0, 0.0, 0.0, 0.0)):
+        L = lib()
+        L.orc_full_create.restype = C.c_void_p
+        self.xf = np.ascontiguousarray(xf, dtype=np.float64)
+        self.yf = np.ascontiguousarray(yf, dtype=np.float64)
+        self.nx, self.ny = self.xf.size + 1, self.yf.size + 1
+        bu = np.ascontiguousarray(bc_u, dtype=np.float64)      # W, E, S, N
+        bv = np.ascontiguousarray(bc_v, dtype=np.float64)
+        self.h = C.c_void_p(L.orc_full_create(self.nx, self.ny, P(self.xf), P(self.yf), C.c_double(dt), C.c_double(Re),
+                                              ad_itermax, ppe_itermax, C.c_double(ad_tol), C.c_double(ppe_tol), ppe_abs,
+                                              P(bu), P(bv)))
+        self.stats = np.zeros(8)
+
+    def close(self):
+        if self.h:
+            lib().orc_full_destroy(self.h)
+            self.h = None
+
+    def set_bodies(self, bodies, velocities=None):
+        offs = np.zeros(len(bodies) + 1, dtype=np.int32)
+        for b, m in enumerate(bodies):
+            offs[b + 1] = offs[b] + len(m)
+        xm = np.ascontiguousarray(np.concatenate([np.asarray(m, dtype=np.float64)[:, 0] for m in bodies]))
+        ym = np.ascontiguousarray(np.concatenate([np.asarray(m, dtype=np.float64)[:, 1] for m in bodies]))
+        ub = vb = None
+        if velocities is not None:
+            ub = np.ascontiguousarray([v[0] for v in velocities], dtype=np.float64)
+            vb = np.ascontiguousarray([v[1] for v in velocities], dtype=np.float64)
+        lib().orc_full_set_bodies(self.h, len(bodies), PI(offs), P(xm), P(ym), P(ub) if ub is not None else None,
+                                  P(vb) if vb is not None else None)
+
+    def update_ib(self):
+        return lib().orc_full_update_ib(self.h)
+
+    def get(self, name):
+        n = {"uf": (self.nx - 1) * (self.ny - 2), "vf": (self.nx - 2) * (self.ny - 1)}.get(name, self.nx * self.ny)
+        out = np.zeros(n)
+        assert lib().orc_full_get(self.h, FIELD[name], P(out)) == 0
+        return out
+
+    def set(self, name, a):
+        a = np.ascontiguousarray(a, dtype=np.float64).reshape(-1)
+        assert lib().orc_full_set(self.h, FIELD[name], P(a)) == 0
+
+    def predictor(self):
+        lib().orc_full_predictor(self.h, P(self.stats)); return self.stats.copy()
+
+    def poisson(self):
+        lib().orc_full_poisson(self.h, P(self.stats)); return self.stats.copy()
+
+    def correct(self):
+        lib().orc_full_correct(self.h)
+
+    def step(self):
+        lib().orc_full_step(self.h, P(self.stats)); return self.stats.copy()
+
+    def ghost_cells(self):
+        n = lib().orc_full_ghost_cells(self.h, None, None, None, None, None)
+        cell = np.zeros(n, dtype=np.int32); sten = np.zeros((n, 4), dtype=np.int32)
+        w = np.zeros((n, 10)); bi = np.zeros((n, 2)); ip = np.zeros((n, 2))
+        if n:
+            lib().orc_full_ghost_cells(self.h, PI(cell), PI(sten.reshape(-1)), P(w.reshape(-1)), P(bi.reshape(-1)), P(ip.reshape(-1)))
+        return {"cell": cell, "stencil": sten, "weights": w, "bi": bi, "ip": ip}
