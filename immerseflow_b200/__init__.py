@@ -357,7 +357,7 @@ class ImmerseFlow:
 
     # ---- multi-GPU ------------------------------------------------------------------------------
     def ipc_export(self) -> bytes:
-        buf = C.create_string_buffer(64)
+        buf = C.create_string_buffer(128)
         self._check(self.lib.ifx_ipc_export(self._h, buf), "ifx_ipc_export")
         return buf.raw
 

@@ -31,6 +31,7 @@ SOURCES = [
     ("kernels_v4.cu", True),
     ("kernels_reduce.cu", True),
     ("kernels_misc.cu", True),
+    ("kernels_halo.cu", True),
     ("kernels_full.cu", True),
     ("kernels_ib.cu", True),
     ("kernels_ic.cu", False),   # default flags on purpose: same libdevice expansion as the reference build

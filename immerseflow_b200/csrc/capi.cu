@@ -190,6 +190,79 @@ double ifx::rounding_band(const ifx_solver* s, size_t nblocks, int rows_per_cta)
 }
 
 // ------------------------------------------------------------------------------------------------
+// slabs: halo context of a launch, generic halo exchange, waits
+// ------------------------------------------------------------------------------------------------
+static XchgSync* peer_sync(ifx_solver* s, int r) {
+  const size_t off = (6 * s->peer_field_elems[r] * sizeof(double) + 255) / 256 * 256;
+  return reinterpret_cast<XchgSync*>(reinterpret_cast<char*>(s->peer_seg[r]) + off);
+}
+static double* peer_field(ifx_solver* s, int r, int field_index) {
+  return reinterpret_cast<double*>(s->peer_seg[r]) + (size_t)field_index * s->peer_field_elems[r];
+}
+
+// field_index: 0,1 = u[0],u[1]; 2,3 = v[0],v[1]; 4,5 = p[0],p[1]
+void ifx::make_halo_ctx(ifx_solver* s, int group, int nfields, const int* out_field_index, HaloCtx* hx) {
+  std::memset(hx, 0, sizeof(*hx));
+  hx->nranks = s->connected ? s->opt.nranks : 1;
+  hx->rank = s->opt.rank;
+  if (hx->nranks == 1) return;
+  const int r = s->opt.rank;
+  hx->has_lo = r > 0;
+  hx->has_hi = r < s->opt.nranks - 1;
+  hx->seq = ++s->seq[group];
+  hx->mseq = ++s->mseq;
+  hx->wait_lo = s->sync->flags[group][0];
+  hx->wait_hi = s->sync->flags[group][1];
+  if (hx->has_lo) {
+    hx->signal_lo = peer_sync(s, r - 1)->flags[group][1];
+    for (int f = 0; f < nfields; f++)
+      hx->peer_row_lo[f] = peer_field(s, r - 1, out_field_index[f]) + (size_t)(s->peer_nyl[r - 1] - 1) * s->L.pitch;
+  }
+  if (hx->has_hi) {
+    hx->signal_hi = peer_sync(s, r + 1)->flags[group][0];
+    for (int f = 0; f < nfields; f++) hx->peer_row_hi[f] = peer_field(s, r + 1, out_field_index[f]);
+  }
+  for (int q = 0; q < s->opt.nranks; q++) {
+    XchgSync* ps = peer_sync(s, q);
+    hx->mail[q] = &ps->mail[0][0][0];
+    hx->mail_seq[q] = &ps->mail_seq[0][0];
+  }
+}
+
+int ifx::halo_wait(ifx_solver* s, int group, unsigned need, int tile_cols) {
+  if (!s->connected || s->opt.nranks == 1) return IFX_OK;
+  const int ntiles = (s->L.nx - 2 + tile_cols - 1) / tile_cols;
+  s->launches++;
+  IFX_CUDA(s, launch_halo_wait(s->opt.rank > 0 ? s->sync->flags[group][0] : nullptr,
+                               s->opt.rank < s->opt.nranks - 1 ? s->sync->flags[group][1] : nullptr, ntiles, need, s->stream));
+  return IFX_OK;
+}
+
+// deliver my first / last owned row of the listed fields to the neighbours, publish, and wait for theirs
+int ifx::halo_exchange(ifx_solver* s, int group, int nfields, const int* field_index, int tile_cols) {
+  if (!s->connected || s->opt.nranks == 1) return IFX_OK;
+  const int r = s->opt.rank;
+  HaloPushArgs a{};
+  a.L = s->L;
+  a.nfields = nfields;
+  a.has_lo = r > 0; a.has_hi = r < s->opt.nranks - 1;
+  a.seq = ++s->seq[group];
+  a.tile_cols = tile_cols;
+  a.ntiles = (s->L.nx - 2 + tile_cols - 1) / tile_cols;
+  if (a.ntiles > IFX_MAX_TILES) return fail(s, IFX_ERR_INVALID, "too many column tiles for the flag array");
+  for (int f = 0; f < nfields; f++) {
+    a.src[f] = peer_field(s, r, field_index[f]);
+    if (a.has_lo) a.dst_lo[f] = peer_field(s, r - 1, field_index[f]) + (size_t)(s->peer_nyl[r - 1] - 1) * s->L.pitch;
+    if (a.has_hi) a.dst_hi[f] = peer_field(s, r + 1, field_index[f]);
+  }
+  if (a.has_lo) a.signal_lo = peer_sync(s, r - 1)->flags[group][1];
+  if (a.has_hi) a.signal_hi = peer_sync(s, r + 1)->flags[group][0];
+  s->launches++;
+  IFX_CUDA(s, launch_halo_push(a, s->stream));
+  return halo_wait(s, group, a.seq, tile_cols);
+}
+
+// ------------------------------------------------------------------------------------------------
 // lifetime
 // ------------------------------------------------------------------------------------------------
 extern "C" int ifx_create(const ifx_input* in, const double* xf, const double* yf,
@@ -245,7 +318,23 @@ extern "C" int ifx_create(const ifx_input* in, const double* xf, const double* y
     IFX_CUDA(s, cudaMemsetAsync(*p, 0, sizeof(double) * s->field_elems, s->stream));
     return IFX_OK;
   };
-  double** fields[] = {&s->u[0], &s->u[1], &s->v[0], &s->v[1], &s->p[0], &s->p[1], &s->sx, &s->sy};
+  if (opt.nranks < 1 || opt.nranks > IFX_MAX_RANKS || opt.rank < 0 || opt.rank >= opt.nranks) {
+    s->err = "bad rank / nranks (1..8 slabs)";
+    return bail(IFX_ERR_INVALID);
+  }
+  // exchange segment: the six ping-pong fields + the synchronisation area, one allocation (see common.cuh)
+  s->sync_off = (6 * s->field_elems * sizeof(double) + 255) / 256 * 256;
+  s->seg_bytes = s->sync_off + sizeof(XchgSync);
+  if (cudaMalloc(&s->seg, s->seg_bytes) != cudaSuccess) { s->err = "cudaMalloc exchange segment"; return bail(IFX_ERR_CUDA); }
+  cudaMemsetAsync(s->seg, 0, s->seg_bytes, s->stream);
+  s->u[0] = s->seg; s->u[1] = s->seg + s->field_elems;
+  s->v[0] = s->seg + 2 * s->field_elems; s->v[1] = s->seg + 3 * s->field_elems;
+  s->p[0] = s->seg + 4 * s->field_elems; s->p[1] = s->seg + 5 * s->field_elems;
+  s->sync = reinterpret_cast<XchgSync*>(reinterpret_cast<char*>(s->seg) + s->sync_off);
+  s->peer_seg[opt.rank] = s->seg;
+  s->peer_field_elems[opt.rank] = s->field_elems;
+  s->peer_nyl[opt.rank] = L.nyl;
+  double** fields[] = {&s->sx, &s->sy};
   for (double** f : fields)
     if ((rc = alloc_field(f)) != IFX_OK) return bail(rc);
   if (opt.compat == IFX_COMPAT_FULL || in->nx > in->ny) {
@@ -281,7 +370,9 @@ extern "C" int ifx_destroy(ifx_solver* s) {
   if (!s) return IFX_OK;
   cudaSetDevice(s->device);
   if (s->stream) cudaStreamSynchronize(s->stream);
-  double* fields[] = {s->u[0], s->u[1], s->v[0], s->v[1], s->p[0], s->p[1], s->sx, s->sy, s->rhs, s->uf, s->vf,
+  for (int r = 0; r < IFX_MAX_RANKS; r++)
+    if (s->peer_seg[r] && r != s->opt.rank) cudaIpcCloseMemHandle(s->peer_seg[r]);
+  double* fields[] = {s->seg, s->sx, s->sy, s->rhs, s->uf, s->vf,
                       s->partials, s->res_a, s->res_b, s->red_partial, s->red_out, s->d_xm, s->d_ym, s->d_ub, s->d_vb,
                       s->d_bbox, s->gc.w_dir, s->gc.w_neu, s->gc.bi, s->gc.ip, s->gc_tmp_a, s->gc_tmp_b};
   for (double* f : fields) if (f) cudaFree(f);
@@ -504,6 +595,13 @@ int ifx::run_ad_loop(ifx_solver* s, ifx_step_stats* st, bool full) {
 
   IFX_CUDA(s, cudaEventRecord(s->ev[0], s->stream));
   const int base = s->cur_uv;
+  const bool slabs = s->connected && s->opt.nranks > 1;
+  const int tw_ad = v4_tile_cols(2, s->tune_ad);
+  if (slabs) {   // halo rows of the starting field (also what the source pass reads)
+    if (s->kernel_variant != 4) return fail(s, IFX_ERR_INVALID, "slabs need the default kernel variant");
+    const int fi[2] = {base, 2 + base};
+    if ((rc = halo_exchange(s, 0, 2, fi, tw_ad)) != IFX_OK) return rc;
+  }
 
   // ---- velf + BC + ADSource (ADSolver.cu:298-311) in one pass
   AdSourceArgs sa{};
@@ -539,14 +637,17 @@ int ifx::run_ad_loop(ifx_solver* s, ifx_step_stats* st, bool full) {
   ja.rows_per_cta = ry;
   ja.rc.itermax = itermax; ja.rc.tol = s->opt.ad_tol; ja.rc.use_second = 1; ja.rc.test_abs = 0;
   ja.rc.decide = exact ? 0 : 1;
-  ja.rc.certify = exact ? 0 : 1;
+  ja.rc.certify = (exact || slabs) ? 0 : 1;     // slabs: the global sum is taken as is (+-1 at the rounding edge)
   ja.rc.band = rounding_band(s, nblocks, ry);
+  unsigned seq_before = s->seq[0];
 
   auto set_iter = [&](int m) {
     const int src = (base + m - 1) & 1;
     ja.uC = s->u[src]; ja.vC = s->v[src];
     ja.uT = s->u[src ^ 1]; ja.vT = s->v[src ^ 1];
     ja.rc.eval_iter = m;
+    const int fo[2] = {src ^ 1, 2 + (src ^ 1)};
+    make_halo_ctx(s, 0, 2, fo, &ja.hx);
   };
 
   int m = 0, fallbacks = 0;
@@ -565,7 +666,7 @@ int ifx::run_ad_loop(ifx_solver* s, ifx_step_stats* st, bool full) {
       if (exact && (rc = exact_decide(s, ja.rc, true)) != IFX_OK) return rc;
     }
     if ((rc = fetch_ctl(s)) != IFX_OK) return rc;
-    if (s->h_ctl->done && s->h_ctl->ambiguous) {
+    if (s->h_ctl->done && s->h_ctl->ambiguous && !slabs) {
       // the fused sum of iteration h_ctl->iter is within rounding of the tolerance: re-evaluate that
       // iteration's residual in the reference's summation order (iterate and predecessor are intact)
       fallbacks++;
@@ -586,6 +687,7 @@ int ifx::run_ad_loop(ifx_solver* s, ifx_step_stats* st, bool full) {
   const int K = s->h_ctl->iter;
   s->cur_uv = (base + K) & 1;
   s->last_ad_iters = K;
+  if (slabs && (rc = halo_wait(s, 0, seq_before + (unsigned)K, tw_ad)) != IFX_OK) return rc;   // rows of iterate K have landed
   if (K == 1 && !full) {   // final buffer's ghost ring was never written this step: give it BC(start field)
     s->launches++;
     IFX_CUDA(s, launch_copy_ring(L, s->u[base], s->u[s->cur_uv], s->v[base], s->v[s->cur_uv], s->stream));
@@ -625,6 +727,9 @@ int ifx::run_ppe_loop(ifx_solver* s, ifx_step_stats* st, bool laplace_ref) {
 
   IFX_CUDA(s, cudaEventRecord(s->ev[2], s->stream));
   const int base = s->cur_p;
+  const bool slabs = s->connected && s->opt.nranks > 1;
+  const int tw_ppe = v4_tile_cols(0, s->tune_ppe);
+  if (slabs && s->kernel_variant != 4) return fail(s, IFX_ERR_INVALID, "slabs need the default kernel variant");
   if (laplace_ref) {
     // set_pressure_BC (PPESolver.cu:164); the ring is then carried through every sweep (:21)
     s->launches += 2;
@@ -633,6 +738,11 @@ int ifx::run_ppe_loop(ifx_solver* s, ifx_step_stats* st, bool laplace_ref) {
   }
   IFX_CUDA(s, cudaMemsetAsync(s->ctl, 0, sizeof(LoopCtl), s->stream));
   int K = 0, fallbacks = 0;
+  if (slabs) {
+    const int fi[1] = {4 + base};
+    if ((rc = halo_exchange(s, 1, 1, fi, tw_ppe)) != IFX_OK) return rc;
+  }
+  const unsigned seq_before = s->seq[1];
   if (itermax > 0) {
     PpeSweepArgs pa{};
     pa.L = L; pa.M = s->M;
@@ -642,12 +752,14 @@ int ifx::run_ppe_loop(ifx_solver* s, ifx_step_stats* st, bool laplace_ref) {
     pa.rc.itermax = itermax; pa.rc.tol = s->opt.ppe_tol; pa.rc.use_second = 0;
     pa.rc.test_abs = s->opt.ppe_abs_residual ? 1 : 0;
     pa.rc.decide = exact ? 0 : 1;
-    pa.rc.certify = exact ? 0 : 1;
+    pa.rc.certify = (exact || slabs) ? 0 : 1;
     pa.rc.band = rounding_band(s, nblocks, ry);
     auto set_sweep = [&](int m) {     // sweep m: iterate m-1 -> iterate m, evaluates residual(iterate m-1)
       const int src = (base + m - 1) & 1;
       pa.pC = s->p[src]; pa.pT = s->p[src ^ 1];
       pa.rc.eval_iter = m - 1;
+      const int fo[1] = {4 + (src ^ 1)};
+      make_halo_ctx(s, 1, 1, fo, &pa.hx);
     };
     int m = 0;
     for (;;) {
@@ -659,7 +771,7 @@ int ifx::run_ppe_loop(ifx_solver* s, ifx_step_stats* st, bool laplace_ref) {
         if (exact && m > 1 && (rc = exact_decide(s, pa.rc, false)) != IFX_OK) return rc;
       }
       if ((rc = fetch_ctl(s)) != IFX_OK) return rc;
-      if (s->h_ctl->done && s->h_ctl->ambiguous) {
+      if (s->h_ctl->done && s->h_ctl->ambiguous && !slabs) {
         fallbacks++;
         if ((rc = ensure_exact_buffers(s)) != IFX_OK) return rc;
         pa.res = s->res_a;
@@ -676,6 +788,7 @@ int ifx::run_ppe_loop(ifx_solver* s, ifx_step_stats* st, bool laplace_ref) {
     }
     K = s->h_ctl->iter;
     s->cur_p = (base + K) & 1;
+    if (slabs && (rc = halo_wait(s, 1, seq_before + (unsigned)K, tw_ppe)) != IFX_OK) return rc;
   }
   if (laplace_ref) {   // PPESolver.cu:195
     s->launches++;

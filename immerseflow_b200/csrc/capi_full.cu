@@ -54,6 +54,9 @@ extern "C" int ifx_set_bodies(ifx_solver* s, int nbodies, const int* offsets, co
   if (rc != IFX_OK) return rc;
   if (nbodies < 0 || nbodies > 63) return fail(s, IFX_ERR_INVALID, "at most 63 bodies (6-bit owner field in the cell type)");
   if (nbodies > 0 && (!offsets || !xm || !ym)) return fail(s, IFX_ERR_INVALID, "null body arrays");
+  if (nbodies > 0 && s->opt.nranks > 1)
+    return fail(s, IFX_ERR_INVALID, "immersed bodies on slabs need two halo rows for the image-point stencils: not built yet "
+                                    "(DESIGN.md, next steps)");
   IFX_CUDA(s, cudaSetDevice(s->device));
   const int nm = nbodies ? offsets[nbodies] : 0;
   for (int b = 0; b < nbodies; b++)
@@ -217,6 +220,10 @@ extern "C" int ifx_ad_solve(ifx_solver* s, ifx_step_stats* st) {
   if (rc != IFX_OK) return rc;
   if ((rc = full_prepare(s)) != IFX_OK) return rc;
   // start-of-step consistency: ring + ghost cells of (u, v); first step: face velocities from the cells
+  if (s->connected && s->opt.nranks > 1) {
+    const int fi[2] = {s->cur_uv, 2 + s->cur_uv};
+    if ((rc = halo_exchange(s, 2, 2, fi, 256)) != IFX_OK) return rc;
+  }
   if ((rc = full_refresh_velocity_bc(s, s->cur_uv)) != IFX_OK) return rc;
   if (!s->faces_valid) {
     s->launches++;
@@ -284,5 +291,50 @@ extern "C" int ifx_step(ifx_solver* s, ifx_step_stats* st) {
   return IFX_OK;
 }
 
-extern "C" int ifx_ipc_export(ifx_solver* s, unsigned char*) { return fail(s, IFX_ERR_INVALID, "multi-GPU not built yet"); }
-extern "C" int ifx_ipc_connect(ifx_solver* s, const unsigned char*, int) { return fail(s, IFX_ERR_INVALID, "multi-GPU not built yet"); }
+// ------------------------------------------------------------------------------------------------
+// slabs: one process per GPU; the launcher all-gathers the blobs (torch.distributed) and hands them back
+// blob: [0,64) cudaIpcMemHandle_t of the exchange segment, [64,72) field_elems, [72,76) nyl, [76,80) pitch,
+//       [80,84) j_begin, [84,88) j_end, [88,92) rank
+// ------------------------------------------------------------------------------------------------
+extern "C" int ifx_ipc_export(ifx_solver* s, unsigned char* blob) {
+  if (!s || !blob) return IFX_ERR_INVALID;
+  IFX_CUDA(s, cudaSetDevice(s->device));
+  std::memset(blob, 0, IFX_IPC_HANDLE_BYTES);
+  cudaIpcMemHandle_t h;
+  IFX_CUDA(s, cudaIpcGetMemHandle(&h, s->seg));
+  static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  std::memcpy(blob, &h, 64);
+  const unsigned long long fe = s->field_elems;
+  std::memcpy(blob + 64, &fe, 8);
+  const int meta[5] = {s->L.nyl, s->L.pitch, s->L.jb, s->L.je, s->opt.rank};
+  std::memcpy(blob + 72, meta, sizeof(meta));
+  return IFX_OK;
+}
+
+extern "C" int ifx_ipc_connect(ifx_solver* s, const unsigned char* all, int nranks) {
+  if (!s || !all) return IFX_ERR_INVALID;
+  if (nranks != s->opt.nranks) return fail(s, IFX_ERR_INVALID, "nranks does not match the options the solver was created with");
+  IFX_CUDA(s, cudaSetDevice(s->device));
+  int prev_je = 1;
+  for (int r = 0; r < nranks; r++) {
+    const unsigned char* b = all + (size_t)r * IFX_IPC_HANDLE_BYTES;
+    unsigned long long fe; int meta[5];
+    std::memcpy(&fe, b + 64, 8);
+    std::memcpy(meta, b + 72, sizeof(meta));
+    if (meta[4] != r) return fail(s, IFX_ERR_INVALID, "blobs are not in rank order");
+    if (meta[1] != s->L.pitch) return fail(s, IFX_ERR_INVALID, "ranks disagree on the row pitch (different nx?)");
+    if (meta[2] != prev_je) return fail(s, IFX_ERR_INVALID, "slabs do not tile the rows contiguously");
+    prev_je = meta[3];
+    s->peer_field_elems[r] = (size_t)fe;
+    s->peer_nyl[r] = meta[0];
+    if (r == s->opt.rank) { s->peer_seg[r] = s->seg; continue; }
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, b, 64);
+    void* p = nullptr;
+    IFX_CUDA(s, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    s->peer_seg[r] = p;
+  }
+  if (prev_je != s->L.ny - 1) return fail(s, IFX_ERR_INVALID, "slabs do not cover all interior rows");
+  s->connected = true;
+  return IFX_OK;
+}

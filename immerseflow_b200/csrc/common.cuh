@@ -82,7 +82,50 @@ struct LoopCtl {
   double hist[2 * 64]; // first 64 iterations' residuals
 };
 
-#define IFX_MAX_PARTIALS_SLOTS 4
+// ---------------------------------------------------------------------------------------------------------
+// Slab decomposition (one process per GPU).  Every rank keeps its exchangeable fields and a small
+// synchronisation area in ONE allocation that its neighbours map through CUDA IPC; halo rows are
+// delivered by plain stores to the mapped peer pointer from inside the sweep kernels (NVLink P2P), followed
+// by a release-store of a sequence number the consumer acquires before it reads the row.
+// ---------------------------------------------------------------------------------------------------------
+#define IFX_MAX_RANKS 8
+#define IFX_MAX_TILES 1024
+#define IFX_SYNC_GROUPS 3          // 0: predictor sweeps (u, v), 1: Poisson sweeps (p), 2: everything else
+#define IFX_MAIL_SLOTS 4
+
+struct XchgSync {
+  unsigned flags[IFX_SYNC_GROUPS][2][IFX_MAX_TILES];      // [group][0: written by lower nbr, 1: by upper][tile]
+  double mail[IFX_MAIL_SLOTS][IFX_MAX_RANKS][2];          // per-rank residual partials of one sweep
+  unsigned mail_seq[IFX_MAIL_SLOTS][IFX_MAX_RANKS];
+};
+
+struct HaloCtx {
+  int nranks, rank;
+  int has_lo, has_hi;              // a neighbour slab below / above
+  unsigned seq;                    // sequence number of this launch within its sync group
+  unsigned mseq;                   // global sweep counter (mailbox slot / tag)
+  const unsigned* wait_lo;         // my flags written by the lower neighbour, per tile
+  const unsigned* wait_hi;
+  unsigned* signal_lo;             // the lower neighbour's "written by upper" flags
+  unsigned* signal_hi;
+  double* peer_row_lo[2];          // lower neighbour's top halo row of the OUTPUT buffer (per field), row start
+  double* peer_row_hi[2];          // upper neighbour's bottom halo row
+  double* mail[IFX_MAX_RANKS];     // every rank's mail[][][] (mine included)
+  unsigned* mail_seq[IFX_MAX_RANKS];
+};
+
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void wait_seq_ge(const unsigned* p, unsigned need) {
+  // sequence numbers wrap after 2^32 launches; compare as a signed distance
+  while ((int)(ld_acquire_sys(p) - need) < 0) { __nanosleep(64); }
+}
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll

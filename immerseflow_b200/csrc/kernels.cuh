@@ -34,6 +34,7 @@ struct AdJacobiArgs {
   double two_bc_u[4], two_bc_v[4];    // 2*bc for W, E, S, N
   int rows_per_cta;
   int force;                          // run even if ctl->done (reference-order re-evaluation)
+  HaloCtx hx;                         // slab neighbours (nranks == 1: unused)
 };
 
 struct AdSourceArgs {
@@ -59,6 +60,7 @@ struct PpeSweepArgs {
   ReduceCfg rc;
   int rows_per_cta;
   int force;
+  HaloCtx hx;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -70,7 +72,7 @@ struct PpeSweepArgs {
 template <int THREADS>
 __device__ __forceinline__ void block_reduce_and_decide(double r0, double r1, double* partials,
                                                         LoopCtl* ctl, const ReduceCfg& rc,
-                                                        unsigned bid, unsigned nblocks) {
+                                                        unsigned bid, unsigned nblocks, const HaloCtx* hx = nullptr) {
   constexpr int NW = THREADS / 32;
   __shared__ double sh[2][NW];
   __shared__ int s_last;
@@ -106,6 +108,26 @@ __device__ __forceinline__ void block_reduce_and_decide(double r0, double r1, do
     a = sh[0][0]; b = sh[1][0];
 #pragma unroll
     for (int w = 1; w < NW; ++w) { a += sh[0][w]; b += sh[1][w]; }
+    if (hx && hx->nranks > 1) {
+      // global residual over the slabs: every rank posts its partial into every rank's mailbox (NVLink P2P
+      // stores), then adds all of them in rank order — same operands, same order, same stop decision everywhere
+      const unsigned slot = hx->mseq & (IFX_MAIL_SLOTS - 1);
+      const unsigned me = (unsigned)hx->rank;
+      for (int r = 0; r < hx->nranks; ++r) {
+        double* m = hx->mail[r] + ((size_t)slot * IFX_MAX_RANKS + me) * 2;
+        m[0] = a; m[1] = b;
+      }
+      __threadfence_system();
+      for (int r = 0; r < hx->nranks; ++r) st_release_sys(hx->mail_seq[r] + slot * IFX_MAX_RANKS + me, hx->mseq);
+      double ga = 0.0, gb = 0.0;
+      for (int r = 0; r < hx->nranks; ++r) {
+        const unsigned* q = hx->mail_seq[me] + slot * IFX_MAX_RANKS + r;
+        while (ld_acquire_sys(q) != hx->mseq) { __nanosleep(64); }
+        const volatile double* m = hx->mail[me] + ((size_t)slot * IFX_MAX_RANKS + r) * 2;
+        ga += m[0]; gb += m[1];
+      }
+      a = ga; b = gb;
+    }
     ctl->ticket = 0;
     ctl->res0 = a;
     ctl->res1 = b;
@@ -171,6 +193,20 @@ cudaError_t launch_gc_pressure(int ngc, const int* cell, const int* stencil, con
                                double* pdst, int gather, cudaStream_t st);
 cudaError_t launch_gc_scatter(int ngc, const int* cell, const double* a, double* qa, const double* b, double* qb,
                               cudaStream_t st);
+// kernels_halo.cu — halo delivery outside the sweep kernels (between stages) and flag waits
+struct HaloPushArgs {
+  Layout L;
+  int nfields;
+  const double* src[4];            // local fields
+  double* dst_lo[4];               // lower neighbour's top-halo row start per field (or null)
+  double* dst_hi[4];
+  int has_lo, has_hi;
+  unsigned seq;
+  unsigned* signal_lo; unsigned* signal_hi;
+  int tile_cols, ntiles;
+};
+cudaError_t launch_halo_push(const HaloPushArgs& a, cudaStream_t st);
+cudaError_t launch_halo_wait(const unsigned* wait_lo, const unsigned* wait_hi, int ntiles, unsigned need, cudaStream_t st);
 // kernels_reduce.cu — the reference's summation order (preSim.cu:12-50, 376-441)
 cudaError_t launch_reduce6(const double* in, size_t n, double* partial, double* out, cudaStream_t st,
                            bool abs_values = false);

@@ -69,12 +69,16 @@ struct ifx_solver {
   double *gc_tmp_a = nullptr, *gc_tmp_b = nullptr;   // gather arrays for in-place ghost-cell refresh
   bool state_bc_fresh = false;       // ring + ghost cells of u, v consistent with the interior
 
-  // multi-GPU exchange
-  void* xchg = nullptr;              // this rank's exchange segment (IPC-exported)
-  size_t xchg_bytes = 0;
-  void* peer_lo = nullptr;           // mapped segment of rank-1 / rank+1
-  void* peer_hi = nullptr;
-  std::vector<void*> peer_all;
+  // exchange segment: u[0..1], v[0..1], p[0..1] + XchgSync in ONE allocation (IPC-exported to the other ranks)
+  double* seg = nullptr;
+  size_t seg_bytes = 0, sync_off = 0;
+  ifx::XchgSync* sync = nullptr;     // inside seg
+  void* peer_seg[IFX_MAX_RANKS] = {};          // mapped segments (own rank: seg)
+  size_t peer_field_elems[IFX_MAX_RANKS] = {};
+  int peer_nyl[IFX_MAX_RANKS] = {};
+  bool connected = false;
+  unsigned seq[IFX_SYNC_GROUPS] = {0, 0, 0};   // launches per sync group (identical on every rank)
+  unsigned mseq = 0;                           // residual-mailbox tag
 
   int kernel_variant = 4;            // 1: register-rolled direct loads (kernels_ad.cu / kernels_ppe.cu, reference mode only)
                                      // 4: bulk-copy row pipeline, lean interior path (kernels_v4.cu, default)
@@ -102,6 +106,10 @@ int run_ad_loop(ifx_solver* s, ifx_step_stats* st, bool full);
 int run_ppe_loop(ifx_solver* s, ifx_step_stats* st, bool laplace_ref);
 int full_refresh_velocity_bc(ifx_solver* s, int buf);
 int full_refresh_pressure_bc(ifx_solver* s, int buf);
+// slabs
+void make_halo_ctx(ifx_solver* s, int group, int nfields, const int* out_field_index, HaloCtx* hx);
+int halo_exchange(ifx_solver* s, int group, int nfields, const int* field_index, int tile_cols);
+int halo_wait(ifx_solver* s, int group, unsigned need, int tile_cols);
 }
 
 #define IFX_CUDA(s, call)                                                                      \

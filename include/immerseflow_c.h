@@ -184,7 +184,7 @@ int ifx_get_ghost_cells(ifx_solver* s, int* cell_id, int* stencil_id, double* we
                         double* bi_xy, double* ip_xy, int capacity);
 
 /* ---- multi-GPU slabs (one process per GPU; halos move over NVLink peer mappings) -------------- */
-#define IFX_IPC_HANDLE_BYTES 64
+#define IFX_IPC_HANDLE_BYTES 128
 /* export this rank's exchange segment; the launcher all-gathers the handles (torch.distributed) */
 int ifx_ipc_export(ifx_solver* s, unsigned char handle[IFX_IPC_HANDLE_BYTES]);
 /* map the neighbours' segments (NULL = domain boundary on that side) and all ranks' mailboxes */
