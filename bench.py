@@ -43,6 +43,8 @@ def parse_args():
     ap.add_argument("--cpu-sample-rows", type=int, default=192, help="rows of the workload the CPU baseline runs on")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--emulate-slab-of", type=int, default=0,
+                    help="diagnostic: run ONE rank's slab of an N-way decomposition on one GPU, no exchange (timing only)")
     return ap.parse_args()
 
 
@@ -148,7 +150,8 @@ def main():
     config = {"workload": f"vortex IC on uniform {args.nx}x{args.ny} cells, reference BCs (u=1,v=0), no immersed body, "
                           f"dt={args.dt}, Re={args.Re}, AD_itermax={args.ad_itermax}, {args.ppe_sweeps} Poisson sweeps/step from a smooth "
                           f"non-zero pressure field",
-              "grid": [args.nx, args.ny], "l2": "working set 17 GB >> 126 MB L2 (no flush needed)"}
+              "grid": [args.nx, args.ny], "l2": "working set 17 GB >> 126 MB L2 (no flush needed)",
+              "decomposition": f"{world} row slab(s), halo rows by in-kernel NVLink P2P stores, residual by P2P mailboxes"}
 
     if args.impl == "reference":
         if rank != 0:
@@ -176,17 +179,24 @@ def main():
     ncx, ncy = args.nx, args.ny
     inp = ifx.make_input(ncx, ncy, args.dt, args.Re, AD_itermax=args.ad_itermax, PPE_itermax=args.ppe_sweeps)
     xf, yf = ifx.uniform_faces(ncx, 1.0), ifx.uniform_faces(ncy, 1.0)
-    if world > 1:
-        raise SystemExit("multi-GPU slabs: not built yet in this revision")
-    s = ifx.ImmerseFlow(inp, xf, yf, device=dev, sweeps_per_batch=args.ppe_sweeps + 1)
+    from immerseflow_b200 import slabs
+    jb, je = slabs.partition_rows(inp.ny, world)[rank]
+    if args.emulate_slab_of and world == 1:
+        jb, je = slabs.partition_rows(inp.ny, args.emulate_slab_of)[0]
+    s = ifx.ImmerseFlow(inp, xf, yf, device=dev, sweeps_per_batch=args.ppe_sweeps + 1, rank=rank, nranks=world,
+                        j_begin=jb, j_end=je)
     s.initializeData()
     # The reference starts the Poisson solve from p == 0 (preSim.cu:67), which makes most quotients exact zeros for
     # the first sweeps — an arithmetic special case.  The bench uses a smooth non-zero pressure field so that every
     # fp64 division takes the normal-operand path a converging solve sees.
     n_p = s.field_size("p")
+    lo = jb - 1
     jj, ii = np.divmod(np.arange(n_p, dtype=np.float64), float(inp.nx))
+    jj += lo
     s.set("p", 50.0 + 40.0 * np.sin(ii * (6.283185307179586 / inp.nx)) * np.cos(jj * (6.283185307179586 / inp.ny)))
     del jj, ii
+    if world > 1:
+        slabs.connect(s, dist)
 
     def barrier():
         if world > 1:
@@ -221,15 +231,16 @@ def main():
         dev_ms, wall_ms = t.tolist()
     else:
         wall_ms = wall * 1e3 / args.steps
-    cells = ncx * ncy
+    cells = ncx * ncy if not args.emulate_slab_of else ncx * (je - jb)
     value = cells / (wall_ms * 1e-3) / 1e6
 
     # ---- roofline of the dominant kernel (k_ad_jacobi: 25 launches/step vs ~51 Poisson launches of 1/3 the bytes)
     peak, peak_src = peaks()
-    ad_launch_ms = float(np.mean(ad_ms)) / (k_ad + 1.0 * 48 / 48) if k_ad else None   # source pass ~ one more sweep
-    jac_bytes = 49.0 * cells                     # read u,v,sx,sy + write u',v' (48 B/cell) + 1 B cell type
+    cells_local = ncx * (je - jb)
+    ad_launch_ms = float(np.mean(ad_ms)) / (k_ad + 2.0) if k_ad else None   # + source pass (measured ~2 sweeps, profiles/)
+    jac_bytes = 49.0 * cells_local               # read u,v,sx,sy + write u',v' (48 B/cell) + 1 B cell type
     ppe_launch_ms = float(np.mean(ppe_ms)) / (k_ppe + 1)
-    ppe_bytes = 16.0 * cells                     # Laplace variant as the reference ships it: read p, write p'
+    ppe_bytes = 16.0 * cells_local               # Laplace variant as the reference ships it: read p, write p'
     ach_ad = jac_bytes / (ad_launch_ms * 1e-3) / 1e9 if ad_launch_ms else 0.0
     ach_ppe = ppe_bytes / (ppe_launch_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": "k_ad_jacobi", "achieved": ach_ad, "peak": peak, "unit": "GB/s",
