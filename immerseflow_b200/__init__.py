@@ -33,7 +33,7 @@ C_ABI_SYMBOLS = [
     "ifx_read_input_file", "ifx_read_grid_file", "ifx_write_results_to_file",
     "ifx_create", "ifx_destroy", "ifx_initialize",
     "ifx_field_size", "ifx_set_field", "ifx_get_field", "ifx_save_field",
-    "ifx_ad_solve", "ifx_ppe_solve", "ifx_correct", "ifx_step", "ifx_reduce_sum",
+    "ifx_ad_solve", "ifx_ppe_solve", "ifx_correct", "ifx_step", "ifx_reduce_sum", "ifx_get_residual_history",
     "ifx_set_bodies", "ifx_iblank_update", "ifx_ghost_cell_count", "ifx_get_ghost_cells",
     "ifx_ipc_export", "ifx_ipc_connect",
     "ifx_set_stream", "ifx_synchronize", "ifx_launch_count",
@@ -111,6 +111,7 @@ def load_library() -> C.CDLL:
     for name in ("ifx_ad_solve", "ifx_ppe_solve", "ifx_correct", "ifx_step", "ifx_iblank_update"):
         getattr(lib, name).argtypes = [vp, C.POINTER(IfxStepStats)]
     lib.ifx_reduce_sum.argtypes = [vp, dp, C.c_size_t, dp]
+    lib.ifx_get_residual_history.argtypes = [vp, dp, C.c_int]
     lib.ifx_set_bodies.argtypes = [vp, C.c_int, ip, dp, dp, dp, dp]
     lib.ifx_ghost_cell_count.argtypes = [vp]
     lib.ifx_get_ghost_cells.argtypes = [vp, ip, ip, dp, dp, dp, C.c_int]
@@ -293,6 +294,11 @@ class ImmerseFlow:
         out = C.c_double()
         self._check(self.lib.ifx_reduce_sum(self._h, _dp(v), v.size, C.byref(out)), "ifx_reduce_sum")
         return out.value
+
+    def residual_history(self) -> np.ndarray:               # the reference's "iter = %d %f %f" lines, ADSolver.cu:369
+        buf = np.zeros(128)
+        n = self.lib.ifx_get_residual_history(self._h, _dp(buf), 64)
+        return buf[:2 * n].reshape(n, 2).copy()
 
     def saveDataToFile(self, field: str, filename: str) -> None:   # postSim.cu:10-39
         self._check(self.lib.ifx_save_field(self._h, FIELD[field], os.fsencode(filename)), "ifx_save_field")

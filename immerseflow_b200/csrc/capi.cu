@@ -687,6 +687,7 @@ int ifx::run_ad_loop(ifx_solver* s, ifx_step_stats* st, bool full) {
   const int K = s->h_ctl->iter;
   s->cur_uv = (base + K) & 1;
   s->last_ad_iters = K;
+  std::memcpy(s->ad_hist, s->h_ctl->hist, sizeof(s->ad_hist));
   if (slabs && (rc = halo_wait(s, 0, seq_before + (unsigned)K, tw_ad)) != IFX_OK) return rc;   // rows of iterate K have landed
   if (K == 1 && !full) {   // final buffer's ghost ring was never written this step: give it BC(start field)
     s->launches++;
@@ -718,8 +719,9 @@ int ifx::run_ppe_loop(ifx_solver* s, ifx_step_stats* st, bool laplace_ref) {
   const Layout& L = s->L;
   const bool exact = s->opt.reduce_mode == IFX_REDUCE_REFERENCE;
   const int itermax = s->in.PPE_itermax;
-  const int ry = rows_per_cta_for(s, 0);
-  const dim3 grid = tile_grid(s, ry, 0);
+  const int pmode = laplace_ref ? 0 : 1;
+  const int ry = rows_per_cta_for(s, pmode);
+  const dim3 grid = tile_grid(s, ry, pmode);
   const size_t nblocks = (size_t)grid.x * grid.y;
   int rc = ensure_partials(s, nblocks);
   if (rc != IFX_OK) return rc;
@@ -728,7 +730,7 @@ int ifx::run_ppe_loop(ifx_solver* s, ifx_step_stats* st, bool laplace_ref) {
   IFX_CUDA(s, cudaEventRecord(s->ev[2], s->stream));
   const int base = s->cur_p;
   const bool slabs = s->connected && s->opt.nranks > 1;
-  const int tw_ppe = v4_tile_cols(0, s->tune_ppe);
+  const int tw_ppe = v4_tile_cols(laplace_ref ? 0 : 1, s->tune_ppe);
   if (slabs && s->kernel_variant != 4) return fail(s, IFX_ERR_INVALID, "slabs need the default kernel variant");
   if (laplace_ref) {
     // set_pressure_BC (PPESolver.cu:164); the ring is then carried through every sweep (:21)

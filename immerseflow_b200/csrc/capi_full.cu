@@ -275,6 +275,13 @@ extern "C" int ifx_correct(ifx_solver* s, ifx_step_stats* st) {
   return IFX_OK;
 }
 
+extern "C" int ifx_get_residual_history(ifx_solver* s, double* pairs, int capacity) {
+  if (!s || !pairs || capacity <= 0) return 0;
+  const int n = std::min(std::min(s->last_ad_iters, 64), capacity);
+  std::memcpy(pairs, s->ad_hist, sizeof(double) * 2 * n);
+  return n;
+}
+
 // one iteration of main()'s time loop (main.cu:93-96)
 extern "C" int ifx_step(ifx_solver* s, ifx_step_stats* st) {
   if (!s) return IFX_ERR_INVALID;

@@ -1,0 +1,147 @@
+// main.cpp — drop-in driver for the reference's `main` (src/main.cu:75-101), host C++ over the C-ABI.
+//
+// With no arguments it does what the reference binary does when run from its src/ directory: read
+// ../inputs/inputs.txt and ../inputs/{x,y}grid.dat2 (the files the reference's code actually opens,
+// preSim.cu:268,281), build the vortex initial condition, write ../results/final_results.dat (iBlank,
+// preSim.cu:217), run `tmax` predictor steps and leave ../results/uc.dat and ../results/vc.dat
+// (ADSolver.cu:378-379) in the reference's Tecplot ASCII format.  Options select the stretched grids,
+// the complete fractional step (--mode full: predictor, Poisson with source term, projection, optional
+// immersed bodies; also writes ../results/p.dat, PPESolver.cu:197) and where files live.
+//
+// Error behaviour follows the reference: a message on stderr and exit(1) (globalVariables.cuh:91-107,
+// main.cu:12-15), here driven by the library's status codes instead of exit() calls inside the library.
+#include "../../include/immerseflow_c.h"
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <string>
+#include <vector>
+
+static void die(const std::string& msg) {
+  std::cerr << msg << std::endl;
+  std::exit(1);
+}
+
+struct Args {
+  std::string input = "../inputs/inputs.txt";
+  std::string xgrid = "../inputs/xgrid.dat2";
+  std::string ygrid = "../inputs/ygrid.dat2";
+  std::string results = "../results";
+  std::string bodies;
+  std::string mode = "reference";
+  long steps = -1;
+  bool write_every_step = false;
+  bool reference_log = false;
+  bool exact = false;
+  int device = 0;
+};
+
+static void usage() {
+  std::cout <<
+      "immerseflow [--input FILE] [--xgrid FILE] [--ygrid FILE] [--stretched] [--results DIR]\n"
+      "            [--mode reference|full] [--bodies FILE] [--steps N] [--write-every-step]\n"
+      "            [--reference-log] [--exact-reduction] [--device K]\n"
+      "  defaults reproduce the reference binary run from src/: ../inputs/inputs.txt, ../inputs/{x,y}grid.dat2,\n"
+      "  tmax predictor steps, ../results/{final_results,uc,vc}.dat.  --stretched picks ../inputs/{x,y}grid.dat.\n"
+      "  --bodies FILE (full mode): `nbodies`, then per body `nmarkers ub vb` and nmarkers lines `x y` (counter-clockwise).\n";
+}
+
+static Args parse(int argc, char** argv) {
+  Args a;
+  for (int k = 1; k < argc; k++) {
+    std::string o = argv[k];
+    auto val = [&]() -> std::string { if (k + 1 >= argc) die("missing value for " + o); return argv[++k]; };
+    if (o == "--input") a.input = val();
+    else if (o == "--xgrid") a.xgrid = val();
+    else if (o == "--ygrid") a.ygrid = val();
+    else if (o == "--stretched") { a.xgrid = "../inputs/xgrid.dat"; a.ygrid = "../inputs/ygrid.dat"; }
+    else if (o == "--results") a.results = val();
+    else if (o == "--bodies") a.bodies = val();
+    else if (o == "--mode") a.mode = val();
+    else if (o == "--steps") a.steps = std::atol(val().c_str());
+    else if (o == "--write-every-step") a.write_every_step = true;
+    else if (o == "--reference-log") a.reference_log = true;
+    else if (o == "--exact-reduction") a.exact = true;
+    else if (o == "--device") a.device = std::atoi(val().c_str());
+    else if (o == "-h" || o == "--help") { usage(); std::exit(0); }
+    else die("unknown option " + o);
+  }
+  if (a.mode != "reference" && a.mode != "full") die("--mode must be reference or full");
+  return a;
+}
+
+static void check(ifx_solver* s, int rc, const char* what) {
+  if (rc != IFX_OK) die(std::string("ImmerseFlow error in ") + what + ": " + ifx_last_error(s));
+}
+
+int main(int argc, char** argv) {
+  const Args a = parse(argc, argv);
+  std::cout << "ImmerseFlow++ fractional-step path, B200-native build (mode: " << a.mode << ")" << std::endl;
+
+  ifx_input in;
+  if (ifx_read_input_file(a.input.c_str(), &in) != IFX_OK) die("Unable to open file: " + a.input);       // main.cu:12-15
+  std::vector<double> xf(in.nxf), yf(in.nyf);
+  if (ifx_read_grid_file(a.xgrid.c_str(), in.nxf, xf.data()) != IFX_OK) die("Error opening xgrid.dat");    // preSim.cu:270
+  if (ifx_read_grid_file(a.ygrid.c_str(), in.nyf, yf.data()) != IFX_OK) die("Error opening ygrid.dat");    // preSim.cu:283
+
+  ifx_options opt;
+  ifx_default_options(&opt);
+  opt.device = a.device;
+  opt.compat = (a.mode == "full") ? IFX_COMPAT_FULL : IFX_COMPAT_REFERENCE;
+  opt.reduce_mode = a.exact ? IFX_REDUCE_REFERENCE : IFX_REDUCE_FUSED;
+  opt.ppe_abs_residual = (a.mode == "full") ? 1 : 0;
+  ifx_solver* s = nullptr;
+  if (ifx_create(&in, xf.data(), yf.data(), &opt, &s) != IFX_OK) die(std::string("ImmerseFlow error in ifx_create: ") + ifx_last_error(nullptr));
+  std::printf("grid %d x %d cells (%d x %d with ghost cells), dt = %g, Re = %g, AD_itermax = %d, PPE_itermax = %d\n",
+              in.nx - 2, in.ny - 2, in.nx, in.ny, in.dt, in.Re, in.AD_itermax, in.PPE_itermax);
+
+  if (!a.bodies.empty()) {
+    if (a.mode != "full") die("--bodies needs --mode full (the reference has no immersed-boundary code to be compatible with)");
+    std::ifstream f(a.bodies);
+    if (!f) die("Unable to open file: " + a.bodies);
+    int nb = 0;
+    f >> nb;
+    std::vector<int> off(1, 0);
+    std::vector<double> xm, ym, ub, vb;
+    for (int b = 0; b < nb; b++) {
+      int n; double u, v;
+      if (!(f >> n >> u >> v)) die("malformed bodies file");
+      ub.push_back(u); vb.push_back(v);
+      for (int k = 0; k < n; k++) { double x, y; if (!(f >> x >> y)) die("malformed bodies file"); xm.push_back(x); ym.push_back(y); }
+      off.push_back((int)xm.size());
+    }
+    check(s, ifx_set_bodies(s, nb, off.data(), xm.data(), ym.data(), ub.data(), vb.data()), "ifx_set_bodies");
+  }
+
+  check(s, ifx_initialize(s), "ifx_initialize");
+  if (a.mode == "full") check(s, ifx_iblank_update(s, nullptr), "ifx_iblank_update");
+  check(s, ifx_save_field(s, IFX_FIELD_IBLANK, (a.results + "/final_results.dat").c_str()), "final_results.dat");   // preSim.cu:217
+
+  const long nsteps = a.steps >= 0 ? a.steps : (long)in.tmax;        // tmax is a step COUNT in the reference (main.cu:93)
+  std::vector<double> hist(2 * 64);
+  for (long step = 0; step < nsteps; step++) {
+    ifx_step_stats st;
+    check(s, ifx_step(s, &st), "ifx_step");
+    if (a.reference_log) {                                           // the reference's own lines, ADSolver.cu:274,313,369
+      std::printf("dt=%f\n________AD slover________\n", in.dt);
+      const int n = ifx_get_residual_history(s, hist.data(), 64);
+      for (int k = 0; k < n; k++) std::printf("iter = %d %f %f\n", k + 1, hist[2 * k], hist[2 * k + 1]);
+    } else if (a.mode == "full") {
+      std::printf("step %ld: predictor %d iterations (%.3e, %.3e), Poisson %d sweeps (residual %.3e), %.3f ms\n", step + 1,
+                  st.ad_iters, st.ad_ures, st.ad_vres, st.ppe_sweeps, st.ppe_residual, st.ms_total);
+    } else {
+      std::printf("step %ld: predictor %d iterations (%.3e, %.3e), %.3f ms\n", step + 1, st.ad_iters, st.ad_ures, st.ad_vres, st.ms_total);
+    }
+    if (a.write_every_step || step == nsteps - 1) {
+      check(s, ifx_save_field(s, IFX_FIELD_U, (a.results + "/uc.dat").c_str()), "uc.dat");       // ADSolver.cu:378
+      check(s, ifx_save_field(s, IFX_FIELD_V, (a.results + "/vc.dat").c_str()), "vc.dat");       // ADSolver.cu:379
+      if (a.mode == "full") check(s, ifx_save_field(s, IFX_FIELD_P, (a.results + "/p.dat").c_str()), "p.dat");   // PPESolver.cu:197
+    }
+  }
+  std::printf("%lld kernel launches\n", ifx_launch_count(s));
+  ifx_destroy(s);
+  return 0;
+}

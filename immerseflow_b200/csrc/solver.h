@@ -86,6 +86,7 @@ struct ifx_solver {
   int tune_ad = 0, tune_ppe = 0;     // pipeline geometry selectors (IFX_TUNE_AD / IFX_TUNE_PPE)
   int rows_override = 0;             // IFX_ROWS_PER_CTA
   int last_ad_iters = 5;
+  double ad_hist[2 * 64] = {};       // (uRes, vRes) per iteration of the last predictor solve
   cudaEvent_t ev[8] = {};
   long long launches = 0;
   std::string err;

@@ -164,6 +164,9 @@ int ifx_correct(ifx_solver* s, ifx_step_stats* stats);
 /* one time step of main()'s loop, src/main.cu:93-96.  IFX_COMPAT_REFERENCE: == ifx_ad_solve.
  * IFX_COMPAT_FULL: IB update (if bodies moved) -> predictor -> PPE -> correction. */
 int ifx_step(ifx_solver* s, ifx_step_stats* stats);
+/* per-iteration (uRes, vRes) of the last predictor solve, what the reference prints as "iter = %d %f %f"
+ * (src/include/ADSolver.cu:369); at most 64 iterations are kept.  Returns the number of pairs written. */
+int ifx_get_residual_history(ifx_solver* s, double* pairs, int capacity);
 /* replaces ImmerseFlow::Reduction(), src/include/preSim.cu:376-445: sum of n doubles (host input),
  * bit-identical summation order */
 int ifx_reduce_sum(ifx_solver* s, const double* host, size_t n, double* out);
