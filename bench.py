@@ -119,29 +119,59 @@ def peaks():
 # ------------------------------------------------------------------------------------------------
 def cpu_reference_arm(args, rows: int, steps: int, warmup: int):
     """The reference has no CPU path; its reported CPU baseline is the OpenMP transcription of its loops
-    (oracle/, `kind: port`), run with every host thread on a bounded row-slab of the same workload."""
+    (oracle/, `kind: port`), run with every host thread on a bounded row-slab of the same workload (same grid
+    width, same parameters, same iteration caps, `rows` of the 16384 rows)."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import _oracle as orc
     import immerseflow_b200 as ifx
     ncx, ncy = args.nx, rows
     xf = ifx.uniform_faces(ncx, 1.0)
     yf = ifx.uniform_faces(args.ny, 1.0)[: ncy + 1]
-    g = orc.Grid(xf, yf)
-    u, v, p = orc.initial_condition(g)
-    pr = orc.Predictor(g, u, v, args.dt, args.Re, args.ad_itermax)
     cores = orc.lib().orc_num_threads()
     times, k_ad, k_ppe = [], 0, 0
-    for it in range(warmup + steps):
-        t0 = time.perf_counter()
-        k_ad, _ = pr.step()
-        k_ppe, p, _ = orc.ppe_solve(g, p, args.ppe_sweeps)
-        if it >= warmup:
-            times.append(time.perf_counter() - t0)
+    if args.mode == "full":
+        fs = orc.FullSolver(xf, yf, args.dt, args.Re, args.ad_itermax, args.ppe_sweeps, ppe_tol=0.0, ppe_abs=1)
+        g = orc.Grid(xf, yf)
+        u, v, p = orc.initial_condition(g)
+        fs.set("u", u); fs.set("v", v)
+        jj, ii = np.divmod(np.arange(g.nx * g.ny, dtype=np.float64), float(g.nx))
+        fs.set("p", 50.0 + 40.0 * np.sin(ii * (6.283185307179586 / g.nx)) * np.cos(jj * (6.283185307179586 / (args.ny + 2))))
+        fs.update_ib()
+        for it in range(warmup + steps):
+            t0 = time.perf_counter()
+            st = fs.step()
+            if it >= warmup:
+                times.append(time.perf_counter() - t0)
+            k_ad, k_ppe = int(st[0]), int(st[3])
+        fs.close()
+    else:
+        g = orc.Grid(xf, yf)
+        u, v, p = orc.initial_condition(g)
+        pr = orc.Predictor(g, u, v, args.dt, args.Re, args.ad_itermax)
+        for it in range(warmup + steps):
+            t0 = time.perf_counter()
+            k_ad, _ = pr.step()
+            k_ppe, p, _ = orc.ppe_solve(g, p, args.ppe_sweeps)
+            if it >= warmup:
+                times.append(time.perf_counter() - t0)
     cells = ncx * ncy
     t = float(np.mean(times))
     return {"value": cells / t / 1e6, "unit": METRIC, "cores": cores, "kind": "port",
-            "sample": f"{ncx}x{ncy}-cell row slab of the workload, {steps} steps (K_AD={k_ad}, {k_ppe} Poisson sweeps), "
-                      f"OpenMP x{cores}", "ms_per_step": t * 1e3}
+            "sample": f"{ncx}x{ncy}-cell row slab of the workload ({args.mode} step), {steps} step(s) "
+                      f"(K_AD={k_ad}, {k_ppe} Poisson sweeps), OpenMP x{cores}", "ms_per_step": t * 1e3}
+
+
+def measured_traffic(kernel: str, nx: int, ny: int):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/r1_traffic.json), valid
+    for the grid it was captured on; None otherwise."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        e = t.get(kernel)
+        if e and e["grid"] == [nx, ny]:
+            return e["dram_bytes_per_launch"]
+    except Exception:
+        pass
+    return None
 
 
 def main():
@@ -161,7 +191,7 @@ def main():
         if rank != 0:
             return
         steps = max(1, min(args.steps, 3))
-        cb = cpu_reference_arm(args, args.cpu_sample_rows, steps, min(args.warmup, 1))
+        cb = cpu_reference_arm(args, max(args.cpu_sample_rows, 768), steps, min(args.warmup, 1))
         line = {"metric": METRIC, "value": cb["value"], "unit": METRIC, "n_gpus": args.gpus, "steps": steps,
                 "warmup": min(args.warmup, 1), "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference", "config": config,
@@ -253,8 +283,9 @@ def main():
     ppe_bytes = float(ppe_b_cell) * cells_local
     ach_ad = jac_bytes / (ad_launch_ms * 1e-3) / 1e9 if ad_launch_ms else 0.0
     ach_ppe = ppe_bytes / (ppe_launch_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "k_ad_jacobi", "achieved": ach_ad, "peak": peak, "unit": "GB/s",
-                "frac": ach_ad / peak, "traffic": None, "peak_source": peak_src,
+    roofline = {"bound": "hbm", "kernel": "k_sweep_v4<predictor Jacobi>", "achieved": ach_ad, "peak": peak, "unit": "GB/s",
+                "frac": ach_ad / peak, "traffic": measured_traffic("k_sweep_v4_ad", ncx, ncy) if world == 1 else None,
+                "peak_source": peak_src,
                 "algorithmic_bytes_per_cell": 49, "ms_per_launch": ad_launch_ms,
                 "poisson": {"kernel": "k_sweep_v4<poisson %s>" % ("general" if full else "laplace"), "achieved": ach_ppe,
                             "frac": ach_ppe / peak, "algorithmic_bytes_per_cell": ppe_b_cell, "ms_per_launch": ppe_launch_ms,

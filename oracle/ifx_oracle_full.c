@@ -543,10 +543,12 @@ int orc_full_poisson(orc_full* s, double* stats) {
   while ((s->ppe_abs ? Rabs : R) > s->ppe_tol && iter < s->PPE_itermax) {
     orc_ppe_sweep_general(nx, ny, cP, cxm, cxp, cym, cyp, s->celltype, s->rhs, pc, pT, NULL);
     double* t = pc; pc = pT; pT = t;
-    memcpy(scratch, pT, N * 8);     /* residual pass must not disturb the retired buffer */
+    /* residual of the new iterate (the reference evaluates it in a second kernel too, PPESolver.cu:182);
+     * `scratch` only absorbs the sweep's p_new output */
     orc_ppe_sweep_general(nx, ny, cP, cxm, cxp, cym, cyp, s->celltype, s->rhs, pc, scratch, res);
     R = orc_Reduction(res, (int)N, tpb, bpg);
-    for (size_t k = 0; k < N; k++) res[k] = fabs(res[k]);
+#pragma omp parallel for
+    for (long k = 0; k < (long)N; k++) res[k] = fabs(res[k]);
     Rabs = orc_Reduction(res, (int)N, tpb, bpg);
     iter++;
   }
