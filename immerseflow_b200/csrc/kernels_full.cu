@@ -10,6 +10,8 @@
 
 namespace ifx {
 
+constexpr int ROWS_PER_BLOCK = 8;
+
 struct FaceCtx {
   Layout L;
   Metrics M;
@@ -92,18 +94,21 @@ static __global__ void k_ppe_rhs(FaceCtx c, const double* __restrict__ u, const 
                                  double* __restrict__ rhs) {
   const Layout& L = c.L;
   const int i = 1 + blockIdx.x * blockDim.x + threadIdx.x;
-  const int j = L.jb + blockIdx.y;
-  if (i > L.nx - 2 || j >= L.je) return;
-  const int jl = j - L.j0;
-  const size_t o = lidx(L, i, jl);
-  double r = 0.0;
-  if (c.ct[o] == IFX_FLUID) {
-    bool open;
-    const double ufe = face_u(c, u, i, jl, &open), ufw = face_u(c, u, i - 1, jl, &open);
-    const double vfn = face_v(c, v, i, jl, j, &open), vfs = face_v(c, v, i, jl - 1, j - 1, &open);
-    r = ((ufe - ufw) / c.M.dx[i] + (vfn - vfs) / c.M.dy[j]) / c.M.dt;
+  if (i > L.nx - 2) return;
+  const int j0 = L.jb + blockIdx.y * ROWS_PER_BLOCK;
+#pragma unroll 2
+  for (int j = j0; j < min(j0 + ROWS_PER_BLOCK, L.je); ++j) {     // consecutive rows: the row read as "north" is reused
+    const int jl = j - L.j0;
+    const size_t o = lidx(L, i, jl);
+    double r = 0.0;
+    if (c.ct[o] == IFX_FLUID) {
+      bool open;
+      const double ufe = face_u(c, u, i, jl, &open), ufw = face_u(c, u, i - 1, jl, &open);
+      const double vfn = face_v(c, v, i, jl, j, &open), vfs = face_v(c, v, i, jl - 1, j - 1, &open);
+      r = ((ufe - ufw) / c.M.dx[i] + (vfn - vfs) / c.M.dy[j]) / c.M.dt;
+    }
+    rhs[o] = r;
   }
-  rhs[o] = r;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -114,47 +119,50 @@ static __global__ void k_correct(FaceCtx c, const double* __restrict__ us, const
                                  double* __restrict__ uf, double* __restrict__ vf) {
   const Layout& L = c.L;
   const int i = 1 + blockIdx.x * blockDim.x + threadIdx.x;
-  const int j = L.jb + blockIdx.y;
-  if (i > L.nx - 2 || j >= L.je) return;
-  const int jl = j - L.j0;
-  const size_t o = lidx(L, i, jl);
+  if (i > L.nx - 2) return;
+  const int jstart = L.jb + blockIdx.y * ROWS_PER_BLOCK;
   const int nxm2 = L.nx - 2, nym2 = L.ny - 2;
   const double dt = c.M.dt;
-  const double pc = p[o];
-  double u_out = us[o], v_out = vs[o];
-  if (c.ct[o] == IFX_FLUID) {
-    const double dx_i = c.M.dx[i], dx_ip1 = c.M.dx[i + 1], dx_im1 = c.M.dx[i - 1];
-    const double dy_j = c.M.dy[j], dy_jp1 = c.M.dy[j + 1], dy_jm1 = c.M.dy[j - 1];
-    const double pW = (i == 1 || c.ct[o - 1] != IFX_FLUID) ? pc : p[o - 1];
-    const double pE = (i == nxm2 || c.ct[o + 1] != IFX_FLUID) ? pc : p[o + 1];
-    const double pS = (j == 1 || c.ct[o - L.pitch] != IFX_FLUID) ? pc : p[o - L.pitch];
-    const double pN = (j == nym2 || c.ct[o + L.pitch] != IFX_FLUID) ? pc : p[o + L.pitch];
-    const double pe = c.M.rcpx[i] * fma(pE, dx_i, pc * dx_ip1);
-    const double pw = c.M.rcpx[i - 1] * fma(pc, dx_im1, pW * dx_i);
-    const double pn = c.M.rcpy[j] * fma(pN, dy_j, pc * dy_jp1);
-    const double ps = c.M.rcpy[j - 1] * fma(pc, dy_jm1, pS * dy_j);
-    u_out = us[o] - dt * ((pe - pw) / dx_i);
-    v_out = vs[o] - dt * ((pn - ps) / dy_j);
-  }
-  un[o] = u_out;
-  vn[o] = v_out;
+#pragma unroll 2
+  for (int j = jstart; j < min(jstart + ROWS_PER_BLOCK, L.je); ++j) {
+    const int jl = j - L.j0;
+    const size_t o = lidx(L, i, jl);
+    const double pc = p[o];
+    double u_out = us[o], v_out = vs[o];
+    if (c.ct[o] == IFX_FLUID) {
+      const double dx_i = c.M.dx[i], dx_ip1 = c.M.dx[i + 1], dx_im1 = c.M.dx[i - 1];
+      const double dy_j = c.M.dy[j], dy_jp1 = c.M.dy[j + 1], dy_jm1 = c.M.dy[j - 1];
+      const double pW = (i == 1 || c.ct[o - 1] != IFX_FLUID) ? pc : p[o - 1];
+      const double pE = (i == nxm2 || c.ct[o + 1] != IFX_FLUID) ? pc : p[o + 1];
+      const double pS = (j == 1 || c.ct[o - L.pitch] != IFX_FLUID) ? pc : p[o - L.pitch];
+      const double pN = (j == nym2 || c.ct[o + L.pitch] != IFX_FLUID) ? pc : p[o + L.pitch];
+      const double pe = c.M.rcpx[i] * fma(pE, dx_i, pc * dx_ip1);
+      const double pw = c.M.rcpx[i - 1] * fma(pc, dx_im1, pW * dx_i);
+      const double pn = c.M.rcpy[j] * fma(pN, dy_j, pc * dy_jp1);
+      const double ps = c.M.rcpy[j - 1] * fma(pc, dy_jm1, pS * dy_j);
+      u_out = us[o] - dt * ((pe - pw) / dx_i);
+      v_out = vs[o] - dt * ((pn - ps) / dy_j);
+    }
+    un[o] = u_out;
+    vn[o] = v_out;
 
-  // faces owned by this cell: east and north; the first column / first owned row also own their west / south face
-  bool open;
-  {
-    double val = face_u(c, us, i, jl, &open);
-    if (open && i <= L.nx - 3) val = val - dt * ((p[o + 1] - pc) * (2.0 * c.M.rcpx[i]));
-    uf[o] = val;
-    if (i == 1) uf[o - 1] = face_u(c, us, 0, jl, &open);          // grid-boundary face: never corrected
-  }
-  {
-    double val = face_v(c, vs, i, jl, j, &open);
-    if (open && j <= L.ny - 3) val = val - dt * ((p[o + L.pitch] - pc) * (2.0 * c.M.rcpy[j]));
-    vf[o] = val;
-    if (j == L.jb) {
-      double vs_ = face_v(c, vs, i, jl - 1, j - 1, &open);
-      if (open && j - 1 >= 1) vs_ = vs_ - dt * ((pc - p[o - L.pitch]) * (2.0 * c.M.rcpy[j - 1]));
-      vf[o - L.pitch] = vs_;
+    // faces owned by this cell: east and north; the first column / first owned row also own their west / south face
+    bool open;
+    {
+      double val = face_u(c, us, i, jl, &open);
+      if (open && i <= L.nx - 3) val = val - dt * ((p[o + 1] - pc) * (2.0 * c.M.rcpx[i]));
+      uf[o] = val;
+      if (i == 1) uf[o - 1] = face_u(c, us, 0, jl, &open);          // grid-boundary face: never corrected
+    }
+    {
+      double val = face_v(c, vs, i, jl, j, &open);
+      if (open && j <= L.ny - 3) val = val - dt * ((p[o + L.pitch] - pc) * (2.0 * c.M.rcpy[j]));
+      vf[o] = val;
+      if (j == L.jb) {
+        double vs_ = face_v(c, vs, i, jl - 1, j - 1, &open);
+        if (open && j - 1 >= 1) vs_ = vs_ - dt * ((pc - p[o - L.pitch]) * (2.0 * c.M.rcpy[j - 1]));
+        vf[o - L.pitch] = vs_;
+      }
     }
   }
 }
@@ -184,16 +192,16 @@ cudaError_t launch_faces_init(const Layout& L, const Metrics& M, const uint8_t* 
 
 cudaError_t launch_ppe_rhs(const Layout& L, const Metrics& M, const uint8_t* ct, const double* ub, const double* vb,
                            const double* u, const double* v, double* rhs, cudaStream_t st) {
-  dim3 g((L.nx - 2 + 127) / 128, L.je - L.jb);
-  k_ppe_rhs<<<g, 128, 0, st>>>(make_ctx(L, M, ct, ub, vb), u, v, rhs);
+  dim3 g((L.nx - 2 + 255) / 256, (L.je - L.jb + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK);
+  k_ppe_rhs<<<g, 256, 0, st>>>(make_ctx(L, M, ct, ub, vb), u, v, rhs);
   return cudaGetLastError();
 }
 
 cudaError_t launch_correct(const Layout& L, const Metrics& M, const uint8_t* ct, const double* ub, const double* vb,
                            const double* us, const double* vs, const double* p, double* un, double* vn, double* uf,
                            double* vf, cudaStream_t st) {
-  dim3 g((L.nx - 2 + 127) / 128, L.je - L.jb);
-  k_correct<<<g, 128, 0, st>>>(make_ctx(L, M, ct, ub, vb), us, vs, p, un, vn, uf, vf);
+  dim3 g((L.nx - 2 + 255) / 256, (L.je - L.jb + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK);
+  k_correct<<<g, 256, 0, st>>>(make_ctx(L, M, ct, ub, vb), us, vs, p, un, vn, uf, vf);
   return cudaGetLastError();
 }
 
