@@ -238,17 +238,20 @@ int ifx::halo_wait(ifx_solver* s, int group, unsigned need, int tile_cols) {
   return IFX_OK;
 }
 
-// deliver my first / last owned row of the listed fields to the neighbours, publish, and wait for theirs
-int ifx::halo_exchange(ifx_solver* s, int group, int nfields, const int* field_index, int tile_cols) {
+// deliver my first / last owned row of the listed fields to the neighbours and publish `seq` of the group.
+// ctl != null: in-loop use, skipped on the device when the loop finished before iteration `iter`.
+int ifx::halo_push(ifx_solver* s, int group, int nfields, const int* field_index, int tile_cols, unsigned seq,
+                   const LoopCtl* ctl, int iter) {
   if (!s->connected || s->opt.nranks == 1) return IFX_OK;
   const int r = s->opt.rank;
   HaloPushArgs a{};
   a.L = s->L;
   a.nfields = nfields;
   a.has_lo = r > 0; a.has_hi = r < s->opt.nranks - 1;
-  a.seq = ++s->seq[group];
+  a.seq = seq;
   a.tile_cols = tile_cols;
   a.ntiles = (s->L.nx - 2 + tile_cols - 1) / tile_cols;
+  a.ctl = ctl; a.iter = iter;
   if (a.ntiles > IFX_MAX_TILES) return fail(s, IFX_ERR_INVALID, "too many column tiles for the flag array");
   for (int f = 0; f < nfields; f++) {
     a.src[f] = peer_field(s, r, field_index[f]);
@@ -259,7 +262,35 @@ int ifx::halo_exchange(ifx_solver* s, int group, int nfields, const int* field_i
   if (a.has_hi) a.signal_hi = peer_sync(s, r + 1)->flags[group][0];
   s->launches++;
   IFX_CUDA(s, launch_halo_push(a, s->stream));
-  return halo_wait(s, group, a.seq, tile_cols);
+  return IFX_OK;
+}
+
+// push + wait for the neighbours' rows.  With nfields == 0 this is a pairwise barrier: everything a neighbour
+// enqueued before its call is complete when the wait kernel lets this stream continue.
+int ifx::halo_exchange(ifx_solver* s, int group, int nfields, const int* field_index, int tile_cols) {
+  if (!s->connected || s->opt.nranks == 1) return IFX_OK;
+  const unsigned seq = ++s->seq[group];
+  int rc = halo_push(s, group, nfields, field_index, tile_cols, seq, nullptr, 0);
+  if (rc != IFX_OK) return rc;
+  return halo_wait(s, group, seq, tile_cols);
+}
+
+// immersed bodies on a slab run: ghost-cell stencils may read the neighbours' memory, and the sweeps defer
+// their flags to a push kernel behind the ghost-cell kernel.  set_bodies is collective, so every rank agrees.
+bool ifx::bodies_on_slabs(const ifx_solver* s) { return s->connected && s->opt.nranks > 1 && s->nbodies > 0; }
+
+// field f0 (and f1) of the neighbours, as the ghost-cell kernels' remote source
+GcPeers ifx::gc_peers(ifx_solver* s, int f0, int f1) {
+  GcPeers pr{};
+  if (!s->connected || s->opt.nranks == 1) return pr;
+  const int r = s->opt.rank;
+  const int f[2] = {f0, f1};
+  for (int k = 0; k < 2; k++) {
+    if (f[k] < 0) continue;
+    if (r > 0) pr.lo[k] = peer_field(s, r - 1, f[k]);
+    if (r < s->opt.nranks - 1) pr.hi[k] = peer_field(s, r + 1, f[k]);
+  }
+  return pr;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -640,6 +671,10 @@ int ifx::run_ad_loop(ifx_solver* s, ifx_step_stats* st, bool full) {
   ja.rc.certify = (exact || slabs) ? 0 : 1;     // slabs: the global sum is taken as is (+-1 at the rounding edge)
   ja.rc.band = rounding_band(s, nblocks, ry);
   unsigned seq_before = s->seq[0];
+  // ghost cells on slabs: sweep -> ghost-cell kernel (reads the neighbours' previous iterate) -> push kernel, which
+  // re-delivers the boundary rows (now with their ghost cells) and only then publishes the sweep's sequence number
+  const bool defer = full && bodies_on_slabs(s);
+  if (defer && ry < IFX_GC_REACH) return fail(s, IFX_ERR_INVALID, "IFX_ROWS_PER_CTA must be >= 4 with bodies on slabs");
 
   auto set_iter = [&](int m) {
     const int src = (base + m - 1) & 1;
@@ -648,6 +683,7 @@ int ifx::run_ad_loop(ifx_solver* s, ifx_step_stats* st, bool full) {
     ja.rc.eval_iter = m;
     const int fo[2] = {src ^ 1, 2 + (src ^ 1)};
     make_halo_ctx(s, 0, 2, fo, &ja.hx);
+    ja.hx.defer = defer ? 1 : 0;
   };
 
   int m = 0, fallbacks = 0;
@@ -660,8 +696,14 @@ int ifx::run_ad_loop(ifx_solver* s, ifx_step_stats* st, bool full) {
       if ((rc = launch_ad_jacobi(s, ja, grid, exact)) != IFX_OK) return rc;
       if (full && s->has_gc) {   // ghost cells of iterate m from iterate m-1 (Jacobi-lagged, like every other cell)
         s->launches++;
+        const int src = (base + m - 1) & 1;
         IFX_CUDA(s, launch_gc_velocity(s->gc.count, s->gc.cell, s->gc.stencil, s->gc.w_dir, s->gc.body, s->d_ub, s->d_vb,
-                                       ja.uC, ja.vC, ja.uT, ja.vT, 0, s->ctl, m, s->stream));
+                                       ja.uC, ja.vC, gc_peers(s, src, 2 + src), ja.uT, ja.vT, 0, s->ctl, m, s->stream));
+      }
+      if (defer) {
+        const int dst = (base + m) & 1;
+        const int fo[2] = {dst, 2 + dst};
+        if ((rc = halo_push(s, 0, 2, fo, tw_ad, ja.hx.seq, s->ctl, m)) != IFX_OK) return rc;
       }
       if (exact && (rc = exact_decide(s, ja.rc, true)) != IFX_OK) return rc;
     }

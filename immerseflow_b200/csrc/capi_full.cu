@@ -11,27 +11,51 @@ using namespace ifx;
 // boundary-condition refresh of a velocity / pressure buffer pair: ghost ring + ghost cells, the ghost cells
 // gathered from the field before any of them is overwritten (oracle: apply_velocity_bc / apply_pressure_bc)
 // ------------------------------------------------------------------------------------------------
+// Slabs with bodies: a stencil may reach into the neighbour's rows, so the gather is fenced pairwise (halo rows
+// delivered and the neighbours' fields complete before they are read; nobody scatters before everybody has
+// gathered) and the boundary rows are re-delivered afterwards, ghost cells included.
+static int slab_barrier(ifx_solver* s) { return halo_exchange(s, 2, 0, nullptr, 256); }
+
 int ifx::full_refresh_velocity_bc(ifx_solver* s, int buf) {
   double tu[4], tv[4];
   fill_bc(s, tu, tv);
+  const bool bs = bodies_on_slabs(s);
+  int rc;
   s->launches += 2;
   IFX_CUDA(s, launch_apply_ring(s->L, s->u[buf], tu, 0, s->stream));
   IFX_CUDA(s, launch_apply_ring(s->L, s->v[buf], tv, 0, s->stream));
+  const int fi[2] = {buf, 2 + buf};
+  if (bs && (rc = halo_exchange(s, 2, 2, fi, 256)) != IFX_OK) return rc;     // fresh halo rows; also the first barrier
   if (s->has_gc) {
-    s->launches += 2;
+    s->launches++;
     IFX_CUDA(s, launch_gc_velocity(s->gc.count, s->gc.cell, s->gc.stencil, s->gc.w_dir, s->gc.body, s->d_ub, s->d_vb,
-                                   s->u[buf], s->v[buf], s->gc_tmp_a, s->gc_tmp_b, 1, nullptr, 0, s->stream));
+                                   s->u[buf], s->v[buf], gc_peers(s, buf, 2 + buf), s->gc_tmp_a, s->gc_tmp_b, 1, nullptr, 0,
+                                   s->stream));
+  }
+  if (bs && (rc = slab_barrier(s)) != IFX_OK) return rc;
+  if (s->has_gc) {
+    s->launches++;
     IFX_CUDA(s, launch_gc_scatter(s->gc.count, s->gc.cell, s->gc_tmp_a, s->u[buf], s->gc_tmp_b, s->v[buf], s->stream));
   }
+  if (bs && (rc = halo_exchange(s, 2, 2, fi, 256)) != IFX_OK) return rc;
   return IFX_OK;
 }
 
 int ifx::full_refresh_pressure_bc(ifx_solver* s, int buf) {
+  const bool bs = bodies_on_slabs(s);
+  int rc;
   s->launches++;
   IFX_CUDA(s, launch_apply_ring(s->L, s->p[buf], nullptr, 1, s->stream));
-  if (s->has_gc) {   // diagnostic only: the solver never reads p at ghost cells (closed-face rule)
-    s->launches += 2;
-    IFX_CUDA(s, launch_gc_pressure(s->gc.count, s->gc.cell, s->gc.stencil, s->gc.w_neu, s->p[buf], s->gc_tmp_a, 1, s->stream));
+  // diagnostic only: the solver never reads p at ghost cells (closed-face rule)
+  if (bs && (rc = slab_barrier(s)) != IFX_OK) return rc;
+  if (s->has_gc) {
+    s->launches++;
+    IFX_CUDA(s, launch_gc_pressure(s->gc.count, s->gc.cell, s->gc.stencil, s->gc.w_neu, s->p[buf], gc_peers(s, 4 + buf, -1),
+                                   s->gc_tmp_a, 1, s->stream));
+  }
+  if (bs && (rc = slab_barrier(s)) != IFX_OK) return rc;
+  if (s->has_gc) {
+    s->launches++;
     IFX_CUDA(s, launch_gc_scatter(s->gc.count, s->gc.cell, s->gc_tmp_a, s->p[buf], nullptr, nullptr, s->stream));
   }
   return IFX_OK;
@@ -54,9 +78,9 @@ extern "C" int ifx_set_bodies(ifx_solver* s, int nbodies, const int* offsets, co
   if (rc != IFX_OK) return rc;
   if (nbodies < 0 || nbodies > 63) return fail(s, IFX_ERR_INVALID, "at most 63 bodies (6-bit owner field in the cell type)");
   if (nbodies > 0 && (!offsets || !xm || !ym)) return fail(s, IFX_ERR_INVALID, "null body arrays");
-  if (nbodies > 0 && s->opt.nranks > 1)
-    return fail(s, IFX_ERR_INVALID, "immersed bodies on slabs need two halo rows for the image-point stencils: not built yet "
-                                    "(DESIGN.md, next steps)");
+  if (nbodies > 0 && s->opt.nranks > 1 && s->L.je - s->L.jb < 2 * IFX_GC_REACH)
+    return fail(s, IFX_ERR_INVALID, "immersed bodies on slabs need at least 8 rows per slab (ghost-cell stencils reach up to "
+                                    "4 rows into the neighbour)");
   IFX_CUDA(s, cudaSetDevice(s->device));
   const int nm = nbodies ? offsets[nbodies] : 0;
   for (int b = 0; b < nbodies; b++)
@@ -148,8 +172,22 @@ extern "C" int ifx_iblank_update(ifx_solver* s, ifx_step_stats* st) {
     IFX_CUDA(s, cudaMalloc(&s->d_bbox, sizeof(double) * 4 * 64));
     IFX_CUDA(s, cudaMemcpy(s->d_body_off, zero, sizeof(zero), cudaMemcpyHostToDevice));
   }
+  const bool slabs = s->opt.nranks > 1;
+  if (slabs && s->nbodies > 0 && !s->connected)
+    return fail(s, IFX_ERR_STATE, "slab run: call ifx_ipc_connect before the bodies are classified (the ghost-cell stencils "
+                                  "address the neighbours' rows)");
+  BodySet B{s->nbodies, s->d_body_off, s->d_xm, s->d_ym, s->d_bbox};
+  SlabGeom sg{};
+  if (slabs && s->connected) {
+    sg.has_lo = s->opt.rank > 0; sg.has_hi = s->opt.rank < s->opt.nranks - 1;
+    if (sg.has_lo) sg.nyl_lo = s->peer_nyl[s->opt.rank - 1];
+    if (sg.has_hi) sg.nyl_hi = s->peer_nyl[s->opt.rank + 1];
+    if ((size_t)std::max(sg.nyl_lo, sg.nyl_hi) * L.pitch >= (1u << 30))
+      return fail(s, IFX_ERR_INVALID, "neighbour slab too large for the 30-bit remote stencil index");
+  }
+  IFX_CUDA(s, cudaMemsetAsync(s->d_counters, 0, sizeof(int) * 4, s->stream));
   s->launches += 4;
-  IFX_CUDA(s, launch_classify(L, s->M.xc, s->M.yc, s->nbodies, s->d_body_off, s->d_xm, s->d_ym, s->d_bbox, s->celltype, s->stream));
+  IFX_CUDA(s, launch_classify(L, s->M.xc, s->M.yc, B, s->celltype, s->stream));
   IFX_CUDA(s, launch_gc_count(L, s->celltype, s->d_rowcount, s->d_rowstart, s->d_counters, s->stream));
   int total = 0;
   IFX_CUDA(s, cudaMemcpyAsync(&total, s->d_counters, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
@@ -159,9 +197,14 @@ extern "C" int ifx_iblank_update(ifx_solver* s, ifx_step_stats* st) {
   s->has_gc = total > 0;
   if (total > 0) {
     s->launches += 2;
-    IFX_CUDA(s, launch_gc_build(L, s->M.xc, s->M.yc, s->d_body_off, s->d_xm, s->d_ym, s->celltype, s->d_rowstart, total,
+    IFX_CUDA(s, launch_gc_build(L, s->M.xc, s->M.yc, B, sg, s->celltype, s->d_rowstart, total,
                                 s->gc.cell, s->gc.ref_id, s->gc.body, s->gc.stencil, s->gc.stencil_ref, s->gc.w_dir,
-                                s->gc.w_neu, s->gc.bi, s->gc.ip, s->stream));
+                                s->gc.w_neu, s->gc.bi, s->gc.ip, s->d_counters + 1, s->stream));
+    int err = 0;
+    IFX_CUDA(s, cudaMemcpyAsync(&err, s->d_counters + 1, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    IFX_CUDA(s, cudaStreamSynchronize(s->stream));
+    if (err) return fail(s, IFX_ERR_INVALID, "a ghost-cell stencil reaches more than 4 rows into (or beyond) the neighbour slab: "
+                                             "use fewer ranks for this grid");
   }
   s->bodies_dirty = false;
   s->faces_valid = false;          // closed faces moved with the bodies

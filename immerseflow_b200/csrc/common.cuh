@@ -92,6 +92,7 @@ struct LoopCtl {
 #define IFX_MAX_TILES 1024
 #define IFX_SYNC_GROUPS 3          // 0: predictor sweeps (u, v), 1: Poisson sweeps (p), 2: everything else
 #define IFX_MAIL_SLOTS 4
+#define IFX_GC_REACH 4             // rows beyond its slab a ghost-cell stencil may read from the neighbour's memory
 
 struct XchgSync {
   unsigned flags[IFX_SYNC_GROUPS][2][IFX_MAX_TILES];      // [group][0: written by lower nbr, 1: by upper][tile]
@@ -103,6 +104,7 @@ struct HaloCtx {
   int nranks, rank;
   int has_lo, has_hi;              // a neighbour slab below / above
   unsigned seq;                    // sequence number of this launch within its sync group
+  int defer;                       // 1: a later kernel publishes this launch's sequence number (ghost cells on slabs)
   unsigned mseq;                   // global sweep counter (mailbox slot / tag)
   const unsigned* wait_lo;         // my flags written by the lower neighbour, per tile
   const unsigned* wait_hi;

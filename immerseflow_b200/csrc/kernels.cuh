@@ -178,19 +178,34 @@ cudaError_t launch_correct(const Layout& L, const Metrics& M, const uint8_t* ct,
                            const double* us, const double* vs, const double* p, double* un, double* vn, double* uf,
                            double* vf, cudaStream_t st);
 // kernels_ib.cu — classification, ghost-cell list and stencils, ghost-cell values
-cudaError_t launch_classify(const Layout& L, const double* xc, const double* yc, int nbodies, const int* off,
-                            const double* xm, const double* ym, const double* bbox, uint8_t* celltype, cudaStream_t st);
+struct BodySet {                   // marker polygons of all bodies (device pointers)
+  int nbodies;
+  const int* off;                  // nbodies+1 offsets into xm / ym
+  const double* xm; const double* ym;
+  const double* bbox;              // [xmin, xmax, ymin, ymax] per body
+};
+struct SlabGeom {                  // what the ghost-cell stencils need to know about the neighbour slabs
+  int has_lo, has_hi;
+  int nyl_lo, nyl_hi;              // rows the neighbours store (their owned rows + 2)
+};
+struct GcPeers {                   // the source field(s) of a ghost-cell evaluation in the neighbours' memory
+  const double* lo[2];
+  const double* hi[2];
+};
+cudaError_t launch_classify(const Layout& L, const double* xc, const double* yc, const BodySet& B, uint8_t* celltype,
+                            cudaStream_t st);
 cudaError_t launch_gc_count(const Layout& L, const uint8_t* celltype, int* rowcount, int* rowstart, int* total,
                             cudaStream_t st);
-cudaError_t launch_gc_build(const Layout& L, const double* xc, const double* yc, const int* off, const double* xm,
-                            const double* ym, const uint8_t* celltype, const int* rowstart, int ngc, int* cell, int* ref_id,
+cudaError_t launch_gc_build(const Layout& L, const double* xc, const double* yc, const BodySet& B, const SlabGeom& sg,
+                            const uint8_t* celltype, const int* rowstart, int ngc, int* cell, int* ref_id,
                             int* body, int* stencil, int* stencil_ref, double* wd, double* wn, double* bi, double* ip,
-                            cudaStream_t st);
+                            int* err, cudaStream_t st);
 cudaError_t launch_gc_velocity(int ngc, const int* cell, const int* stencil, const double* wd, const int* body,
-                               const double* ub, const double* vb, const double* usrc, const double* vsrc, double* udst,
-                               double* vdst, int gather, const LoopCtl* ctl, int iter, cudaStream_t st);
+                               const double* ub, const double* vb, const double* usrc, const double* vsrc,
+                               const GcPeers& pr, double* udst, double* vdst, int gather, const LoopCtl* ctl, int iter,
+                               cudaStream_t st);
 cudaError_t launch_gc_pressure(int ngc, const int* cell, const int* stencil, const double* wn, const double* psrc,
-                               double* pdst, int gather, cudaStream_t st);
+                               const GcPeers& pr, double* pdst, int gather, cudaStream_t st);
 cudaError_t launch_gc_scatter(int ngc, const int* cell, const double* a, double* qa, const double* b, double* qb,
                               cudaStream_t st);
 // kernels_halo.cu — halo delivery outside the sweep kernels (between stages) and flag waits
@@ -204,6 +219,8 @@ struct HaloPushArgs {
   unsigned seq;
   unsigned* signal_lo; unsigned* signal_hi;
   int tile_cols, ntiles;
+  const LoopCtl* ctl;              // in-loop use: skip when the loop finished before iteration `iter` (else null)
+  int iter;
 };
 cudaError_t launch_halo_push(const HaloPushArgs& a, cudaStream_t st);
 cudaError_t launch_halo_wait(const unsigned* wait_lo, const unsigned* wait_hi, int ntiles, unsigned need, cudaStream_t st);

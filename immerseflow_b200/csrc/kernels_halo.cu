@@ -8,6 +8,7 @@
 namespace ifx {
 
 static __global__ void k_halo_push(HaloPushArgs a) {
+  if (a.ctl && a.ctl->done && a.ctl->iter < a.iter) return;
   const Layout& L = a.L;
   const int b = blockIdx.x;
   // tile b covers interior columns [1 + b*TW, 1 + (b+1)*TW); the first / last tile also carry the ghost columns

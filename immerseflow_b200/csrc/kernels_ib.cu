@@ -27,42 +27,55 @@ __device__ __forceinline__ bool point_in_polygon(double x, double y, const doubl
 
 // a16: SOLID when the cell centre is inside a body polygon; the ghost ring of the grid stays FLUID.
 // bbox = per-body [xmin, xmax, ymin, ymax]: a centre outside the box cannot be inside the polygon, so skipping the
-// crossing test there does not change the result.
-static __global__ void k_classify(Layout L, const double* __restrict__ xc, const double* __restrict__ yc, int nbodies,
-                                  const int* __restrict__ off, const double* __restrict__ xm,
-                                  const double* __restrict__ ym, const double* __restrict__ bbox,
+// crossing test there does not change the result.  A pure function of (i, j) and the geometry: every rank of a
+// slab run can evaluate it for rows it does not store and get the owner's answer.
+__device__ __forceinline__ uint8_t classify_cell(const Layout& L, const double* __restrict__ xc,
+                                                 const double* __restrict__ yc, const BodySet& B, int i, int j) {
+  if (!(i > 0 && i < L.nx - 1 && j > 0 && j < L.ny - 1)) return IFX_FLUID;
+  const double x = xc[i], y = yc[j];
+  for (int b = 0; b < B.nbodies; b++) {
+    if (x < B.bbox[4 * b] || x > B.bbox[4 * b + 1] || y < B.bbox[4 * b + 2] || y > B.bbox[4 * b + 3]) continue;
+    if (point_in_polygon(x, y, B.xm + B.off[b], B.ym + B.off[b], B.off[b + 1] - B.off[b])) return (uint8_t)(b << 2);
+  }
+  return IFX_FLUID;
+}
+
+// full cell type (ghost bit included) of a cell outside the rows this rank stores
+__device__ uint8_t celltype_of(const Layout& L, const double* __restrict__ xc, const double* __restrict__ yc,
+                               const BodySet& B, int i, int j) {
+  const uint8_t c = classify_cell(L, xc, yc, B, i, j);
+  if (c == IFX_FLUID) return c;
+  if (classify_cell(L, xc, yc, B, i - 1, j) == IFX_FLUID || classify_cell(L, xc, yc, B, i + 1, j) == IFX_FLUID ||
+      classify_cell(L, xc, yc, B, i, j - 1) == IFX_FLUID || classify_cell(L, xc, yc, B, i, j + 1) == IFX_FLUID)
+    return c | IFX_GHOST;
+  return c;
+}
+
+static __global__ void k_classify(Layout L, const double* __restrict__ xc, const double* __restrict__ yc, BodySet B,
                                   uint8_t* __restrict__ celltype) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int jl = blockIdx.y;
   if (i >= L.nx || jl >= L.nyl) return;
-  const int j = L.j0 + jl;
-  uint8_t t = IFX_FLUID;
-  if (i > 0 && i < L.nx - 1 && j > 0 && j < L.ny - 1) {
-    const double x = xc[i], y = yc[j];
-    for (int b = 0; b < nbodies; b++) {
-      if (x < bbox[4 * b] || x > bbox[4 * b + 1] || y < bbox[4 * b + 2] || y > bbox[4 * b + 3]) continue;
-      if (point_in_polygon(x, y, xm + off[b], ym + off[b], off[b + 1] - off[b])) { t = (uint8_t)(b << 2); break; }
-    }
-  }
-  celltype[lidx(L, i, jl)] = t;
+  celltype[lidx(L, i, jl)] = classify_cell(L, xc, yc, B, i, L.j0 + jl);
 }
 
 // ghost cell = non-fluid cell with a fluid 4-neighbour.  In place: only 0 -> 2 transitions in the type bits,
 // and the test looks for == FLUID, so concurrent marking cannot change anybody's answer.
-// (slab note: rows jb-1 and je are halo rows classified above with the same rule, so neighbours are complete.)
-static __global__ void k_mark_ghost(Layout L, uint8_t* __restrict__ celltype) {
+// Halo rows of a slab get the owner's answer too: the neighbour row this rank does not store is classified
+// in line.
+static __global__ void k_mark_ghost(Layout L, const double* __restrict__ xc, const double* __restrict__ yc, BodySet B,
+                                    uint8_t* __restrict__ celltype) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int jl = blockIdx.y;
   if (i >= L.nx || jl >= L.nyl) return;
   const int j = L.j0 + jl;
   if (!(i > 0 && i < L.nx - 1 && j > 0 && j < L.ny - 1)) return;
-  if (jl == 0 || jl == L.nyl - 1) return;       // halo rows of a slab: owned by the neighbour rank
   const size_t o = lidx(L, i, jl);
   const uint8_t c = celltype[o];
   if (c == IFX_FLUID || (c & 3) == IFX_GHOST) return;
-  if (celltype[o - 1] == IFX_FLUID || celltype[o + 1] == IFX_FLUID || celltype[o - L.pitch] == IFX_FLUID ||
-      celltype[o + L.pitch] == IFX_FLUID)
-    celltype[o] = c | IFX_GHOST;
+  const bool south = (jl > 0) ? celltype[o - L.pitch] == IFX_FLUID : classify_cell(L, xc, yc, B, i, j - 1) == IFX_FLUID;
+  const bool north = (jl < L.nyl - 1) ? celltype[o + L.pitch] == IFX_FLUID : classify_cell(L, xc, yc, B, i, j + 1) == IFX_FLUID;
+  if (celltype[o - 1] == IFX_FLUID || celltype[o + 1] == IFX_FLUID || south || north) celltype[o] = c | IFX_GHOST;
 }
 
 // ordered compaction, pass 1: ghost cells per owned row
@@ -149,14 +162,22 @@ __device__ __forceinline__ int lower_index(const double* __restrict__ c, int n, 
 }
 
 // a17: one thread per ghost cell — body intercept, image point, enclosing box, weights (oracle: orc_ghost_cells)
-static __global__ void k_gc_geometry(Layout L, const double* __restrict__ xc, const double* __restrict__ yc,
-                                     const int* __restrict__ off, const double* __restrict__ xm,
-                                     const double* __restrict__ ym, const uint8_t* __restrict__ celltype, int ngc,
+//
+// Slabs: a stencil node in a row this rank does not store is read from the owner's memory when the ghost-cell
+// values are evaluated (NVLink P2P load).  Its stencil entry is then negative: -(1 + index in the owner's field),
+// bit 30 of the index selecting the upper neighbour; its cell type is recomputed from the geometry.  A node more
+// than IFX_GC_REACH rows beyond the slab raises *err (the sweep kernels only fence that many rows, kernels_v4.cu).
+static __global__ void k_gc_geometry(Layout L, const double* __restrict__ xc, const double* __restrict__ yc, BodySet B,
+                                     SlabGeom sg, const uint8_t* __restrict__ celltype, int ngc,
                                      const int* __restrict__ ref_id, const int* __restrict__ body,
                                      int* __restrict__ stencil, int* __restrict__ stencil_ref, double* __restrict__ wd,
-                                     double* __restrict__ wn, double* __restrict__ bi, double* __restrict__ ip) {
+                                     double* __restrict__ wn, double* __restrict__ bi, double* __restrict__ ip,
+                                     int* __restrict__ err) {
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= ngc) return;
+  const int* off = B.off;
+  const double* xm = B.xm;
+  const double* ym = B.ym;
   const int id = ref_id[g];
   const int i = id % L.nx, j = id / L.nx;
   const int b = body[g];
@@ -187,13 +208,27 @@ static __global__ void k_gc_geometry(Layout L, const double* __restrict__ xc, co
   const int ni[4] = {i0, i0 + 1, i0, i0 + 1}, nj[4] = {j0, j0, j0 + 1, j0 + 1};
   double w[4] = {(1.0 - a) * (1.0 - bb), a * (1.0 - bb), (1.0 - a) * bb, a * bb};
   double W = 0.0, ws = 0.0;
-  int nid[4];
+  int nid[4], code[4];
   for (int m = 0; m < 4; m++) {
     nid[m] = ni[m] + nj[m] * L.nx;
-    // the stencil may reach one row into the neighbour slab: rows outside [j0, j0+nyl) are clamped
-    int jl = nj[m] - L.j0;
-    jl = jl < 0 ? 0 : (jl > L.nyl - 1 ? L.nyl - 1 : jl);
-    const uint8_t c = celltype[lidx(L, ni[m], jl)];
+    const int jl = nj[m] - L.j0;
+    uint8_t c;
+    if (jl >= 0 && jl < L.nyl) {
+      code[m] = (int)lidx(L, ni[m], jl);
+      c = celltype[code[m]];
+    } else {
+      c = celltype_of(L, xc, yc, B, ni[m], nj[m]);
+      code[m] = 0;
+      if (jl < 0) {                                   // owned by the lower neighbour: its stored rows start at jb_lo - 1
+        const int jp = nj[m] - (L.jb - sg.nyl_lo + 1);
+        if (!sg.has_lo || jp < 1 || nj[m] < L.jb - IFX_GC_REACH) *err = 1;
+        else code[m] = -(1 + (int)((size_t)jp * L.pitch + IFX_PADL + ni[m]));
+      } else {                                        // upper neighbour: its stored rows start at je - 1
+        const int jp = nj[m] - (L.je - 1);
+        if (!sg.has_hi || jp > sg.nyl_hi - 2 || nj[m] > L.je - 1 + IFX_GC_REACH) *err = 1;
+        else code[m] = -(1 + (int)(0x40000000u | (unsigned)((size_t)jp * L.pitch + IFX_PADL + ni[m])));
+      }
+    }
     if (nid[m] != id && (c & 3) == IFX_SOLID) w[m] = 0.0;
     W = W + w[m];
   }
@@ -207,9 +242,7 @@ static __global__ void k_gc_geometry(Layout L, const double* __restrict__ xc, co
   ip[2 * g] = xi; ip[2 * g + 1] = yi;
   for (int m = 0; m < 4; m++) {
     stencil_ref[4 * g + m] = nid[m];
-    int jl = nj[m] - L.j0;
-    jl = jl < 0 ? 0 : (jl > L.nyl - 1 ? L.nyl - 1 : jl);
-    stencil[4 * g + m] = (int)lidx(L, ni[m], jl);
+    stencil[4 * g + m] = code[m];
   }
   if (kept == 0 || (1.0 - ws) < 1e-12) {
     for (int m = 0; m < 4; m++) { wd[5 * g + m] = 0.0; wn[4 * g + m] = 0.0; }
@@ -227,43 +260,52 @@ static __global__ void k_gc_geometry(Layout L, const double* __restrict__ xc, co
 // ghost-cell values.  Dirichlet (u, v): phi = cd*phi_BI + sum wd[m]*phi_m;  Neumann (p): phi = sum wn[m]*phi_m.
 // dst may be another buffer (in-loop, Jacobi-lagged) or a gather array (in-place refresh = eval + scatter).
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ double gc_dirichlet(const double* __restrict__ q, const int* __restrict__ st,
-                                               const double* __restrict__ wd, double phi_bi) {
+__device__ __forceinline__ double gc_node(const double* __restrict__ q, const double* qlo, const double* qhi, int code) {
+  if (code >= 0) return q[code];
+  const unsigned c = (unsigned)(-(code + 1));
+  const double* p = (c & 0x40000000u) ? qhi + (c & 0x3fffffffu) : qlo + c;
+  double v;           // the owner's memory over NVLink: never through a non-coherent cache
+  asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__device__ __forceinline__ double gc_dirichlet(const double* __restrict__ q, const double* qlo, const double* qhi,
+                                               const int* __restrict__ st, const double* __restrict__ wd, double phi_bi) {
   double t = wd[4] * phi_bi;
-  t = fma(wd[0], q[st[0]], t);
-  t = fma(wd[1], q[st[1]], t);
-  t = fma(wd[2], q[st[2]], t);
-  t = fma(wd[3], q[st[3]], t);
+  t = fma(wd[0], gc_node(q, qlo, qhi, st[0]), t);
+  t = fma(wd[1], gc_node(q, qlo, qhi, st[1]), t);
+  t = fma(wd[2], gc_node(q, qlo, qhi, st[2]), t);
+  t = fma(wd[3], gc_node(q, qlo, qhi, st[3]), t);
   return t;
 }
 
 static __global__ void k_gc_velocity(int ngc, const int* __restrict__ cell, const int* __restrict__ stencil,
                                      const double* __restrict__ wd, const int* __restrict__ body,
                                      const double* __restrict__ ub, const double* __restrict__ vb,
-                                     const double* __restrict__ usrc, const double* __restrict__ vsrc,
+                                     const double* __restrict__ usrc, const double* __restrict__ vsrc, GcPeers pr,
                                      double* __restrict__ udst, double* __restrict__ vdst, int gather,
                                      const LoopCtl* ctl, int iter) {
   // in-loop use: iteration `iter` ran iff the loop was not already finished by an earlier iteration
   if (ctl && ctl->done && ctl->iter < iter) return;
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= ngc) return;
-  const double pu = gc_dirichlet(usrc, stencil + 4 * g, wd + 5 * g, ub[body[g]]);
-  const double pv = gc_dirichlet(vsrc, stencil + 4 * g, wd + 5 * g, vb[body[g]]);
+  const double pu = gc_dirichlet(usrc, pr.lo[0], pr.hi[0], stencil + 4 * g, wd + 5 * g, ub[body[g]]);
+  const double pv = gc_dirichlet(vsrc, pr.lo[1], pr.hi[1], stencil + 4 * g, wd + 5 * g, vb[body[g]]);
   const int o = gather ? g : cell[g];
   udst[o] = pu; vdst[o] = pv;
 }
 
 static __global__ void k_gc_pressure(int ngc, const int* __restrict__ cell, const int* __restrict__ stencil,
-                                     const double* __restrict__ wn, const double* __restrict__ psrc,
+                                     const double* __restrict__ wn, const double* __restrict__ psrc, GcPeers pr,
                                      double* __restrict__ pdst, int gather) {
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= ngc) return;
   const int* st = stencil + 4 * g;
   const double* w = wn + 4 * g;
-  double t = w[0] * psrc[st[0]];
-  t = fma(w[1], psrc[st[1]], t);
-  t = fma(w[2], psrc[st[2]], t);
-  t = fma(w[3], psrc[st[3]], t);
+  double t = w[0] * gc_node(psrc, pr.lo[0], pr.hi[0], st[0]);
+  t = fma(w[1], gc_node(psrc, pr.lo[0], pr.hi[0], st[1]), t);
+  t = fma(w[2], gc_node(psrc, pr.lo[0], pr.hi[0], st[2]), t);
+  t = fma(w[3], gc_node(psrc, pr.lo[0], pr.hi[0], st[3]), t);
   pdst[gather ? g : cell[g]] = t;
 }
 
@@ -278,11 +320,11 @@ static __global__ void k_gc_scatter(int ngc, const int* __restrict__ cell, const
 // ---------------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------------
-cudaError_t launch_classify(const Layout& L, const double* xc, const double* yc, int nbodies, const int* off,
-                            const double* xm, const double* ym, const double* bbox, uint8_t* celltype, cudaStream_t st) {
+cudaError_t launch_classify(const Layout& L, const double* xc, const double* yc, const BodySet& B, uint8_t* celltype,
+                            cudaStream_t st) {
   dim3 g((L.nx + 127) / 128, L.nyl);
-  k_classify<<<g, 128, 0, st>>>(L, xc, yc, nbodies, off, xm, ym, bbox, celltype);
-  k_mark_ghost<<<g, 128, 0, st>>>(L, celltype);
+  k_classify<<<g, 128, 0, st>>>(L, xc, yc, B, celltype);
+  k_mark_ghost<<<g, 128, 0, st>>>(L, xc, yc, B, celltype);
   return cudaGetLastError();
 }
 
@@ -294,30 +336,31 @@ cudaError_t launch_gc_count(const Layout& L, const uint8_t* celltype, int* rowco
   return cudaGetLastError();
 }
 
-cudaError_t launch_gc_build(const Layout& L, const double* xc, const double* yc, const int* off, const double* xm,
-                            const double* ym, const uint8_t* celltype, const int* rowstart, int ngc, int* cell, int* ref_id,
+cudaError_t launch_gc_build(const Layout& L, const double* xc, const double* yc, const BodySet& B, const SlabGeom& sg,
+                            const uint8_t* celltype, const int* rowstart, int ngc, int* cell, int* ref_id,
                             int* body, int* stencil, int* stencil_ref, double* wd, double* wn, double* bi, double* ip,
-                            cudaStream_t st) {
+                            int* err, cudaStream_t st) {
   if (ngc <= 0) return cudaSuccess;
   k_gc_fill<<<L.nyl - 2, 256, 0, st>>>(L, celltype, rowstart, ngc, cell, ref_id, body);
-  k_gc_geometry<<<(ngc + 127) / 128, 128, 0, st>>>(L, xc, yc, off, xm, ym, celltype, ngc, ref_id, body, stencil, stencil_ref,
-                                                   wd, wn, bi, ip);
+  k_gc_geometry<<<(ngc + 127) / 128, 128, 0, st>>>(L, xc, yc, B, sg, celltype, ngc, ref_id, body, stencil, stencil_ref,
+                                                   wd, wn, bi, ip, err);
   return cudaGetLastError();
 }
 
 cudaError_t launch_gc_velocity(int ngc, const int* cell, const int* stencil, const double* wd, const int* body,
-                               const double* ub, const double* vb, const double* usrc, const double* vsrc, double* udst,
-                               double* vdst, int gather, const LoopCtl* ctl, int iter, cudaStream_t st) {
+                               const double* ub, const double* vb, const double* usrc, const double* vsrc,
+                               const GcPeers& pr, double* udst, double* vdst, int gather, const LoopCtl* ctl, int iter,
+                               cudaStream_t st) {
   if (ngc <= 0) return cudaSuccess;
-  k_gc_velocity<<<(ngc + 127) / 128, 128, 0, st>>>(ngc, cell, stencil, wd, body, ub, vb, usrc, vsrc, udst, vdst, gather, ctl,
-                                                   iter);
+  k_gc_velocity<<<(ngc + 127) / 128, 128, 0, st>>>(ngc, cell, stencil, wd, body, ub, vb, usrc, vsrc, pr, udst, vdst, gather,
+                                                   ctl, iter);
   return cudaGetLastError();
 }
 
 cudaError_t launch_gc_pressure(int ngc, const int* cell, const int* stencil, const double* wn, const double* psrc,
-                               double* pdst, int gather, cudaStream_t st) {
+                               const GcPeers& pr, double* pdst, int gather, cudaStream_t st) {
   if (ngc <= 0) return cudaSuccess;
-  k_gc_pressure<<<(ngc + 127) / 128, 128, 0, st>>>(ngc, cell, stencil, wn, psrc, pdst, gather);
+  k_gc_pressure<<<(ngc + 127) / 128, 128, 0, st>>>(ngc, cell, stencil, wn, psrc, pr, pdst, gather);
   return cudaGetLastError();
 }
 

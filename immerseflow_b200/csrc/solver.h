@@ -63,7 +63,7 @@ struct ifx_solver {
   bool bodies_dirty = false;
   bool has_gc = false;
   GhostCells gc;
-  int* d_counters = nullptr;         // [0] ghost-cell total
+  int* d_counters = nullptr;         // [0] ghost-cell total, [1] stencil out of reach of the neighbour slab
   int* d_rowcount = nullptr;         // nyl entries
   int* d_rowstart = nullptr;         // nyl + 1 entries
   double *gc_tmp_a = nullptr, *gc_tmp_b = nullptr;   // gather arrays for in-place ghost-cell refresh
@@ -110,6 +110,10 @@ int full_refresh_pressure_bc(ifx_solver* s, int buf);
 // slabs
 void make_halo_ctx(ifx_solver* s, int group, int nfields, const int* out_field_index, HaloCtx* hx);
 int halo_exchange(ifx_solver* s, int group, int nfields, const int* field_index, int tile_cols);
+int halo_push(ifx_solver* s, int group, int nfields, const int* field_index, int tile_cols, unsigned seq,
+              const LoopCtl* ctl, int iter);
+bool bodies_on_slabs(const ifx_solver* s);
+GcPeers gc_peers(ifx_solver* s, int f0, int f1);
 int halo_wait(ifx_solver* s, int group, unsigned need, int tile_cols);
 }
 
