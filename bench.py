@@ -46,6 +46,9 @@ def parse_args():
     ap.add_argument("--mode", default="full", choices=["full", "reference"],
                     help="full: complete fractional step (predictor + Poisson with source + projection); reference: what the "
                          "reference binary's time step runs (predictor) + its Laplace-Jacobi Poisson kernels")
+    ap.add_argument("--bodies", type=int, default=8,
+                    help="moving immersed bodies (BASELINE.json configs[4]: multiple complex-shaped bodies on 16384x16384, iBlank "
+                         "and ghost cells recomputed every step); 0 = no body")
     ap.add_argument("--emulate-slab-of", type=int, default=0,
                     help="diagnostic: run ONE rank's slab of an N-way decomposition on one GPU, no exchange (timing only)")
     return ap.parse_args()
@@ -116,6 +119,25 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def bodies_at(nb: int, step: int, dt: float):
+    """nb lobed closed polygons (256 markers each) on a lattice over the unit square, translating with a constant
+    velocity each: marker arrays + body velocities.  The same arrays go to the CUDA path and to the CPU arm."""
+    if nb <= 0:
+        return [], []
+    cols = int(np.ceil(np.sqrt(nb)))
+    rows = (nb + cols - 1) // cols
+    th = 2.0 * np.pi * np.arange(256) / 256
+    out, vel = [], []
+    for b in range(nb):
+        cx, cy = (b % cols + 0.5) / cols, (b // cols + 0.5) / rows
+        r0 = 0.22 / max(cols, rows)
+        ub, vb = 0.05 * (1 if b % 2 == 0 else -1), 0.03 * (1 if (b // 2) % 2 == 0 else -1)
+        r = r0 * (1.0 + 0.25 * np.cos((3 + b % 4) * th + 0.3 * b))
+        out.append(np.ascontiguousarray(np.stack([cx + ub * dt * step + r * np.cos(th), cy + vb * dt * step + r * np.sin(th)], axis=1)))
+        vel.append((ub, vb))
+    return out, vel
+
+
 # ------------------------------------------------------------------------------------------------
 def cpu_reference_arm(args, rows: int, steps: int, warmup: int):
     """The reference has no CPU path; its reported CPU baseline is the OpenMP transcription of its loops
@@ -126,7 +148,12 @@ def cpu_reference_arm(args, rows: int, steps: int, warmup: int):
     import immerseflow_b200 as ifx
     ncx, ncy = args.nx, rows
     xf = ifx.uniform_faces(ncx, 1.0)
-    yf = ifx.uniform_faces(args.ny, 1.0)[: ncy + 1]
+    r0 = 0
+    if args.bodies > 0 and args.mode == "full":      # the slab that cuts through the first lattice row of bodies
+        cols = int(np.ceil(np.sqrt(args.bodies)))
+        nrow = (args.bodies + cols - 1) // cols
+        r0 = max(0, min(args.ny - ncy, int(0.5 / nrow * args.ny) - ncy // 2))
+    yf = ifx.uniform_faces(args.ny, 1.0)[r0: r0 + ncy + 1]
     cores = orc.lib().orc_num_threads()
     times, k_ad, k_ppe = [], 0, 0
     if args.mode == "full":
@@ -139,6 +166,10 @@ def cpu_reference_arm(args, rows: int, steps: int, warmup: int):
         fs.update_ib()
         for it in range(warmup + steps):
             t0 = time.perf_counter()
+            if args.bodies > 0:
+                b, vel = bodies_at(args.bodies, it, args.dt)
+                fs.set_bodies(b, vel)
+                fs.update_ib()
             st = fs.step()
             if it >= warmup:
                 times.append(time.perf_counter() - t0)
@@ -157,7 +188,7 @@ def cpu_reference_arm(args, rows: int, steps: int, warmup: int):
     cells = ncx * ncy
     t = float(np.mean(times))
     return {"value": cells / t / 1e6, "unit": METRIC, "cores": cores, "kind": "port",
-            "sample": f"{ncx}x{ncy}-cell row slab of the workload ({args.mode} step), {steps} step(s) "
+            "sample": f"{ncx}x{ncy}-cell row slab (rows {r0}..{r0 + ncy}) of the workload ({args.mode} step), {steps} step(s) "
                       f"(K_AD={k_ad}, {k_ppe} Poisson sweeps), OpenMP x{cores}", "ms_per_step": t * 1e3}
 
 
@@ -180,8 +211,11 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
+    nb = args.bodies if args.mode == "full" else 0
+    body_txt = (f"{nb} moving lobed bodies (256 markers each), iBlank + ghost cells recomputed every step" if nb
+                else "no immersed body")
     config = {"mode": args.mode,
-              "workload": f"vortex IC on uniform {args.nx}x{args.ny} cells, reference BCs (u=1,v=0), no immersed body, "
+              "workload": f"vortex IC on uniform {args.nx}x{args.ny} cells, reference BCs (u=1,v=0), {body_txt}, "
                           f"dt={args.dt}, Re={args.Re}, AD_itermax={args.ad_itermax}, {args.ppe_sweeps} Poisson sweeps/step from a smooth "
                           f"non-zero pressure field",
               "grid": [args.nx, args.ny], "l2": "working set 17 GB >> 126 MB L2 (no flush needed)",
@@ -239,8 +273,14 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    step_no = [0]
+
     def one_step():
         if full:
+            if nb:
+                b, vel = bodies_at(nb, step_no[0], args.dt)
+                s.set_bodies(b, vel)
+                step_no[0] += 1
             st = s.step()
             return st, st
         a = s.ADsolver()
@@ -254,16 +294,17 @@ def main():
     sampler.start()
     l0 = s.launch_count
     t0 = time.perf_counter()
-    ad_ms, ppe_ms, cor_ms, k_ad, k_ppe = [], [], [], 0, 0
+    ad_ms, ppe_ms, cor_ms, ib_ms, k_ad, k_ppe = [], [], [], [], 0, 0
     for _ in range(args.steps):
         a, b = one_step()
-        ad_ms.append(a.ms_ad); ppe_ms.append(b.ms_ppe); cor_ms.append(b.ms_correct); k_ad, k_ppe = a.ad_iters, b.ppe_sweeps
+        ad_ms.append(a.ms_ad); ppe_ms.append(b.ms_ppe); cor_ms.append(b.ms_correct); ib_ms.append(b.ms_ib)
+        k_ad, k_ppe = a.ad_iters, b.ppe_sweeps
     barrier()
     wall = time.perf_counter() - t0
     launches = s.launch_count - l0
     clocks = sampler.stop()
     # device time of the step = CUDA-event stage timers (both stages run on the solver's stream back to back)
-    dev_ms = float(np.mean(ad_ms) + np.mean(ppe_ms))
+    dev_ms = float(np.mean(ad_ms) + np.mean(ppe_ms) + np.mean(cor_ms) + np.mean(ib_ms))
     if world > 1:
         t = torch.tensor([dev_ms, wall * 1e3 / args.steps], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -290,7 +331,8 @@ def main():
                 "poisson": {"kernel": "k_sweep_v4<poisson %s>" % ("general" if full else "laplace"), "achieved": ach_ppe,
                             "frac": ach_ppe / peak, "algorithmic_bytes_per_cell": ppe_b_cell, "ms_per_launch": ppe_launch_ms,
                             "sweeps_per_s": 1e3 / ppe_launch_ms},
-                "projection_ms": float(np.mean(cor_ms))}
+                "projection_ms": float(np.mean(cor_ms)), "iblank_ghost_cells_ms": float(np.mean(ib_ms)),
+                "ghost_cells": int(s.lib.ifx_ghost_cell_count(s._h))}
 
     # ---- e2e: same step through the C-ABI with HOST buffers (pinned): H2D of u,v,p, step, D2H of u,v,p
     e2e = None

@@ -718,6 +718,12 @@ int ifx::run_ad_loop(ifx_solver* s, ifx_step_stats* st, bool full) {
       set_iter(m);
       ja.force = 1; ja.rc.decide = 0;
       if ((rc = launch_ad_jacobi(s, ja, grid, true)) != IFX_OK) return rc;
+      if (full && s->has_gc) {   // the sweep leaves throw-away values at ghost cells: restore iterate m's closure
+        const int src = (base + m - 1) & 1;
+        s->launches++;
+        IFX_CUDA(s, launch_gc_velocity(s->gc.count, s->gc.cell, s->gc.stencil, s->gc.w_dir, s->gc.body, s->d_ub, s->d_vb,
+                                       ja.uC, ja.vC, gc_peers(s, src, 2 + src), ja.uT, ja.vT, 0, nullptr, 0, s->stream));
+      }
       if ((rc = exact_decide(s, ja.rc, true)) != IFX_OK) return rc;
       ja.rc.decide = 1;
       if ((rc = fetch_ctl(s)) != IFX_OK) return rc;

@@ -186,9 +186,9 @@ extern "C" int ifx_iblank_update(ifx_solver* s, ifx_step_stats* st) {
       return fail(s, IFX_ERR_INVALID, "neighbour slab too large for the 30-bit remote stencil index");
   }
   IFX_CUDA(s, cudaMemsetAsync(s->d_counters, 0, sizeof(int) * 4, s->stream));
-  s->launches += 4;
-  IFX_CUDA(s, launch_classify(L, s->M.xc, s->M.yc, B, s->celltype, s->stream));
-  IFX_CUDA(s, launch_gc_count(L, s->celltype, s->d_rowcount, s->d_rowstart, s->d_counters, s->stream));
+  s->launches += 2;
+  IFX_CUDA(s, launch_classify(L, s->M.xc, s->M.yc, B, s->celltype, s->d_rowcount, s->stream));
+  IFX_CUDA(s, launch_gc_count(L, s->d_rowcount, s->d_rowstart, s->d_counters, s->stream));
   int total = 0;
   IFX_CUDA(s, cudaMemcpyAsync(&total, s->d_counters, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
   IFX_CUDA(s, cudaStreamSynchronize(s->stream));
@@ -248,9 +248,9 @@ extern "C" int ifx_get_ghost_cells(ifx_solver* s, int* cell_id, int* stencil_id,
 // ------------------------------------------------------------------------------------------------
 // stage entry points
 // ------------------------------------------------------------------------------------------------
-static int full_prepare(ifx_solver* s) {
+static int full_prepare(ifx_solver* s, ifx_step_stats* st = nullptr) {
   int rc;
-  if (s->bodies_dirty && (rc = ifx_iblank_update(s, nullptr)) != IFX_OK) return rc;
+  if (s->bodies_dirty && (rc = ifx_iblank_update(s, st)) != IFX_OK) return rc;
   return IFX_OK;
 }
 
@@ -261,7 +261,7 @@ extern "C" int ifx_ad_solve(ifx_solver* s, ifx_step_stats* st) {
   if (s->opt.compat == IFX_COMPAT_REFERENCE) return run_ad_loop(s, st, false);
   int rc = require_full(s, "predictor");
   if (rc != IFX_OK) return rc;
-  if ((rc = full_prepare(s)) != IFX_OK) return rc;
+  if ((rc = full_prepare(s, st)) != IFX_OK) return rc;
   // start-of-step consistency: ring + ghost cells of (u, v); first step: face velocities from the cells
   if (s->connected && s->opt.nranks > 1) {
     const int fi[2] = {s->cur_uv, 2 + s->cur_uv};

@@ -193,9 +193,8 @@ struct GcPeers {                   // the source field(s) of a ghost-cell evalua
   const double* hi[2];
 };
 cudaError_t launch_classify(const Layout& L, const double* xc, const double* yc, const BodySet& B, uint8_t* celltype,
-                            cudaStream_t st);
-cudaError_t launch_gc_count(const Layout& L, const uint8_t* celltype, int* rowcount, int* rowstart, int* total,
-                            cudaStream_t st);
+                            int* rowcount, cudaStream_t st);
+cudaError_t launch_gc_count(const Layout& L, const int* rowcount, int* rowstart, int* total, cudaStream_t st);
 cudaError_t launch_gc_build(const Layout& L, const double* xc, const double* yc, const BodySet& B, const SlabGeom& sg,
                             const uint8_t* celltype, const int* rowstart, int ngc, int* cell, int* ref_id,
                             int* body, int* stencil, int* stencil_ref, double* wd, double* wn, double* bi, double* ip,

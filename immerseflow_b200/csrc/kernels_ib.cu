@@ -51,46 +51,117 @@ __device__ uint8_t celltype_of(const Layout& L, const double* __restrict__ xc, c
   return c;
 }
 
-static __global__ void k_classify(Layout L, const double* __restrict__ xc, const double* __restrict__ yc, BodySet B,
-                                  uint8_t* __restrict__ celltype) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int jl = blockIdx.y;
-  if (i >= L.nx || jl >= L.nyl) return;
-  celltype[lidx(L, i, jl)] = classify_cell(L, xc, yc, B, i, L.j0 + jl);
+// ---------------------------------------------------------------------------------------------------------
+// Classification, ghost marking and the per-row ghost-cell count in ONE pass that only writes: one block per
+// stored row.  The crossing test of point_in_polygon compares x with xi = xa + (y-ya)*(xb-xa)/(yb-ya), which
+// does not depend on x: the block evaluates the straddling edges of rows j-1, j, j+1 once (a few entries per
+// body), and every cell of the row then answers "first body containing me" and "is a 4-neighbour fluid" by
+// counting x < xi over those short lists — the same comparisons on the same doubles as classify_cell, hence the
+// same bytes as the cell-by-cell definition (the fallback below, used when a list overflows).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int XCAP = 768;            // crossings kept per row
+
+struct RowCrossings {
+  double xi[3][XCAP];
+  unsigned char body[3][XCAP];
+  int n[3];
+  double lo[3], hi[3];               // min / max xi of a row: outside, every parity is even
+};
+
+__device__ __forceinline__ uint8_t classify_from_row(const Layout& L, const double* __restrict__ xc, const BodySet& B,
+                                                     const RowCrossings& rc, int r, int jr, int i) {
+  if (!(i > 0 && i < L.nx - 1 && jr > 0 && jr < L.ny - 1)) return IFX_FLUID;
+  const double x = xc[i];
+  if (rc.n[r] == 0 || !(x < rc.hi[r])) return IFX_FLUID;
+  unsigned long long odd = 0ull;
+  for (int e = 0; e < rc.n[r]; e++)
+    if (x < rc.xi[r][e]) odd ^= 1ull << rc.body[r][e];
+  while (odd) {
+    const int b = __ffsll((long long)odd) - 1;
+    if (!(x < B.bbox[4 * b] || x > B.bbox[4 * b + 1])) return (uint8_t)(b << 2);
+    odd &= odd - 1;
+  }
+  return IFX_FLUID;
 }
 
-// ghost cell = non-fluid cell with a fluid 4-neighbour.  In place: only 0 -> 2 transitions in the type bits,
-// and the test looks for == FLUID, so concurrent marking cannot change anybody's answer.
-// Halo rows of a slab get the owner's answer too: the neighbour row this rank does not store is classified
-// in line.
-static __global__ void k_mark_ghost(Layout L, const double* __restrict__ xc, const double* __restrict__ yc, BodySet B,
-                                    uint8_t* __restrict__ celltype) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int jl = blockIdx.y;
-  if (i >= L.nx || jl >= L.nyl) return;
+static __global__ void __launch_bounds__(256)
+k_classify_rows(Layout L, const double* __restrict__ xc, const double* __restrict__ yc, BodySet B,
+                uint8_t* __restrict__ celltype, int* __restrict__ rowcount) {
+  __shared__ RowCrossings rc;
+  __shared__ int overflow;
+  __shared__ int warp_cnt[8];
+  const int jl = blockIdx.x;
   const int j = L.j0 + jl;
-  if (!(i > 0 && i < L.nx - 1 && j > 0 && j < L.ny - 1)) return;
-  const size_t o = lidx(L, i, jl);
-  const uint8_t c = celltype[o];
-  if (c == IFX_FLUID || (c & 3) == IFX_GHOST) return;
-  const bool south = (jl > 0) ? celltype[o - L.pitch] == IFX_FLUID : classify_cell(L, xc, yc, B, i, j - 1) == IFX_FLUID;
-  const bool north = (jl < L.nyl - 1) ? celltype[o + L.pitch] == IFX_FLUID : classify_cell(L, xc, yc, B, i, j + 1) == IFX_FLUID;
-  if (celltype[o - 1] == IFX_FLUID || celltype[o + 1] == IFX_FLUID || south || north) celltype[o] = c | IFX_GHOST;
-}
-
-// ordered compaction, pass 1: ghost cells per owned row
-static __global__ void k_gc_count_rows(Layout L, const uint8_t* __restrict__ celltype, int* __restrict__ rowcount) {
-  const int jl = 1 + blockIdx.x;                 // owned local rows 1 .. nyl-2
-  int n = 0;
-  for (int i = 1 + threadIdx.x; i < L.nx - 1; i += blockDim.x) n += ((celltype[lidx(L, i, jl)] & 3) == IFX_GHOST);
-  __shared__ int sh[32];
-  for (int off = 16; off > 0; off >>= 1) n += __shfl_down_sync(0xffffffffu, n, off);
-  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = n;
+  if (threadIdx.x < 3) { rc.n[threadIdx.x] = 0; }
+  if (threadIdx.x == 0) overflow = 0;
   __syncthreads();
-  if (threadIdx.x == 0) {
+  for (int r = 0; r < 3; r++) {
+    const int jr = j - 1 + r;
+    if (jr < 1 || jr > L.ny - 2) continue;
+    const double y = yc[jr];
+    for (int b = 0; b < B.nbodies; b++) {
+      if (y < B.bbox[4 * b + 2] || y > B.bbox[4 * b + 3]) continue;         // classify_cell skips the body
+      const double* xm = B.xm + B.off[b];
+      const double* ym = B.ym + B.off[b];
+      const int n = B.off[b + 1] - B.off[b];
+      for (int k = threadIdx.x; k < n; k += blockDim.x) {
+        const int k2 = (k + 1 == n) ? 0 : k + 1;
+        const double xa = xm[k], ya = ym[k], xb = xm[k2], yb = ym[k2];
+        if ((ya > y) != (yb > y)) {
+          const double xi = xa + (y - ya) * (xb - xa) / (yb - ya);
+          const int e = atomicAdd(&rc.n[r], 1);
+          if (e < XCAP) { rc.xi[r][e] = xi; rc.body[r][e] = (unsigned char)b; } else overflow = 1;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    const int r = threadIdx.x;
+    double lo = INFINITY, hi = -INFINITY;
+    const int n = min(rc.n[r], XCAP);
+    for (int e = 0; e < n; e++) { lo = fmin(lo, rc.xi[r][e]); hi = fmax(hi, rc.xi[r][e]); }
+    rc.lo[r] = lo; rc.hi[r] = hi;
+  }
+  __syncthreads();
+  const bool slow = overflow != 0;
+  const bool interior_row = j > 0 && j < L.ny - 1;
+  int ghosts = 0;
+  uint8_t* row = celltype + (size_t)jl * L.pitch;
+  for (int c = threadIdx.x; c * 16 < L.pitch; c += blockDim.x) {           // 16 bytes per thread: cells 16c-15 .. 16c
+    unsigned w[4] = {0x01010101u, 0x01010101u, 0x01010101u, 0x01010101u};  // padding and the ring are FLUID
+    const int ibase = 16 * c - IFX_PADL;
+    const bool maybe = interior_row && (slow || (rc.n[1] > 0 && xc[max(ibase, 0)] < rc.hi[1] &&
+                                                 !(xc[min(ibase + 15, L.nx - 1)] < rc.lo[1])));
+    if (maybe) {
+#pragma unroll 1
+      for (int k = 0; k < 16; k++) {
+        const int i = ibase + k;
+        if (i < 1 || i > L.nx - 2) continue;
+        uint8_t t;
+        if (slow) {
+          t = celltype_of(L, xc, yc, B, i, j);                 // the cell-by-cell definition
+        } else {
+          t = classify_from_row(L, xc, B, rc, 1, j, i);
+          if (t != IFX_FLUID &&
+              (classify_from_row(L, xc, B, rc, 1, j, i - 1) == IFX_FLUID || classify_from_row(L, xc, B, rc, 1, j, i + 1) == IFX_FLUID ||
+               classify_from_row(L, xc, B, rc, 0, j - 1, i) == IFX_FLUID || classify_from_row(L, xc, B, rc, 2, j + 1, i) == IFX_FLUID))
+            t |= IFX_GHOST;
+        }
+        ghosts += ((t & 3) == IFX_GHOST);
+        w[k >> 2] = (w[k >> 2] & ~(0xffu << (8 * (k & 3)))) | ((unsigned)t << (8 * (k & 3)));
+      }
+    }
+    *reinterpret_cast<uint4*>(row + 16 * c) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+  // ordered compaction, pass 1: ghost cells per owned row
+  for (int off = 16; off > 0; off >>= 1) ghosts += __shfl_down_sync(0xffffffffu, ghosts, off);
+  if ((threadIdx.x & 31) == 0) warp_cnt[threadIdx.x >> 5] = ghosts;
+  __syncthreads();
+  if (threadIdx.x == 0 && jl >= 1 && jl <= L.nyl - 2) {
     int t = 0;
-    for (int w = 0; w < (int)(blockDim.x >> 5); w++) t += sh[w];
-    rowcount[blockIdx.x] = t;
+    for (int wv = 0; wv < 8; wv++) t += warp_cnt[wv];
+    rowcount[jl - 1] = t;
   }
 }
 
@@ -120,30 +191,51 @@ static __global__ void k_gc_scan_rows(int nrows, const int* __restrict__ rowcoun
   if (threadIdx.x == 0) { rowstart[nrows] = carry; *total = carry; }
 }
 
-// pass 3: write the ghost cells of each row in increasing i (=> the whole list in increasing reference id)
-static __global__ void k_gc_fill(Layout L, const uint8_t* __restrict__ celltype, const int* __restrict__ rowstart,
-                                 int capacity, int* __restrict__ cell, int* __restrict__ ref_id, int* __restrict__ body) {
+// pass 3: write the ghost cells of each row in increasing i (=> the whole list in increasing reference id).
+// 16 cells (one uint4) per thread; rows without ghost cells leave at once.
+static __global__ void __launch_bounds__(256)
+k_gc_fill(Layout L, const uint8_t* __restrict__ celltype, const int* __restrict__ rowstart,
+          int capacity, int* __restrict__ cell, int* __restrict__ ref_id, int* __restrict__ body) {
   const int jl = 1 + blockIdx.x;
   const int j = L.j0 + jl;
-  __shared__ int warp_tot[32];
+  if (rowstart[blockIdx.x + 1] == rowstart[blockIdx.x]) return;
+  __shared__ int warp_tot[8];
   __shared__ int base;
   if (threadIdx.x == 0) base = rowstart[blockIdx.x];
   __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  for (int i0 = 1; i0 < L.nx - 1; i0 += blockDim.x) {
-    const int i = i0 + threadIdx.x;
-    const uint8_t c = (i < L.nx - 1) ? celltype[lidx(L, i, jl)] : (uint8_t)IFX_FLUID;
-    const bool g = (c & 3) == IFX_GHOST;
-    const unsigned m = __ballot_sync(0xffffffffu, g);
-    if (lane == 0) warp_tot[warp] = __popc(m);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint8_t* row = celltype + (size_t)jl * L.pitch;
+  for (int c0 = 0; c0 * 16 < L.pitch; c0 += 256) {
+    const int c = c0 + threadIdx.x;
+    uint4 v = make_uint4(0x01010101u, 0x01010101u, 0x01010101u, 0x01010101u);
+    if (c * 16 < L.pitch) v = *reinterpret_cast<const uint4*>(row + 16 * c);
+    const unsigned w[4] = {v.x, v.y, v.z, v.w};
+    unsigned gmask = 0;                                   // bit k: cell 16c-15+k is a ghost cell
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+      const unsigned t = (w[k >> 2] >> (8 * (k & 3))) & 0xffu;
+      const int i = 16 * c - IFX_PADL + k;
+      if ((t & 3u) == IFX_GHOST && i >= 1 && i <= L.nx - 2) gmask |= 1u << k;
+    }
+    const int mine = __popc(gmask);
+    int incl = mine;                                      // inclusive scan over the warp
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, off);
+      if (lane >= off) incl += t;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
     __syncthreads();
-    int before = 0;
-    for (int w = 0; w < warp; w++) before += warp_tot[w];
-    int chunk = 0;
-    for (int w = 0; w < nw; w++) chunk += warp_tot[w];
-    if (g) {
-      const int k = base + before + __popc(m & ((1u << lane) - 1u));
-      if (k < capacity) { cell[k] = (int)lidx(L, i, jl); ref_id[k] = i + j * L.nx; body[k] = c >> 2; }
+    int before = 0, chunk = 0;
+    for (int wv = 0; wv < 8; wv++) { if (wv < warp) before += warp_tot[wv]; chunk += warp_tot[wv]; }
+    int k = base + before + incl - mine;
+    while (gmask) {
+      const int b = __ffs(gmask) - 1;
+      gmask &= gmask - 1;
+      const int i = 16 * c - IFX_PADL + b;
+      const unsigned t = (w[b >> 2] >> (8 * (b & 3))) & 0xffu;
+      if (k < capacity) { cell[k] = (int)lidx(L, i, jl); ref_id[k] = i + j * L.nx; body[k] = (int)(t >> 2); }
+      k++;
     }
     __syncthreads();
     if (threadIdx.x == 0) base += chunk;
@@ -321,18 +413,13 @@ static __global__ void k_gc_scatter(int ngc, const int* __restrict__ cell, const
 // launchers
 // ---------------------------------------------------------------------------------------------
 cudaError_t launch_classify(const Layout& L, const double* xc, const double* yc, const BodySet& B, uint8_t* celltype,
-                            cudaStream_t st) {
-  dim3 g((L.nx + 127) / 128, L.nyl);
-  k_classify<<<g, 128, 0, st>>>(L, xc, yc, B, celltype);
-  k_mark_ghost<<<g, 128, 0, st>>>(L, xc, yc, B, celltype);
+                            int* rowcount, cudaStream_t st) {
+  k_classify_rows<<<L.nyl, 256, 0, st>>>(L, xc, yc, B, celltype, rowcount);
   return cudaGetLastError();
 }
 
-cudaError_t launch_gc_count(const Layout& L, const uint8_t* celltype, int* rowcount, int* rowstart, int* total,
-                            cudaStream_t st) {
-  const int nrows = L.nyl - 2;
-  k_gc_count_rows<<<nrows, 256, 0, st>>>(L, celltype, rowcount);
-  k_gc_scan_rows<<<1, 1024, 0, st>>>(nrows, rowcount, rowstart, total);
+cudaError_t launch_gc_count(const Layout& L, const int* rowcount, int* rowstart, int* total, cudaStream_t st) {
+  k_gc_scan_rows<<<1, 1024, 0, st>>>(L.nyl - 2, rowcount, rowstart, total);
   return cudaGetLastError();
 }
 

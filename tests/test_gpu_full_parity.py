@@ -153,6 +153,28 @@ def test_moving_bodies_iblank_recomputed_every_step():
     o.close()
 
 
+def test_comb_body_overflows_the_row_crossing_lists():
+    """A comb with 450 teeth: 900 polygon edges straddle every grid row through the teeth, more than the classifier's
+    per-row crossing list holds, so those rows take the cell-by-cell fallback.  Same bytes either way."""
+    xf, yf = orc.stretched_faces(420, 4.0, 1.01), orc.stretched_faces(90, 2.0, 1.01)
+    g, o = pair(xf, yf, 1e-3, 100.0, 5, 10)
+    teeth = 450
+    xs = np.linspace(3.2, 0.8, 2 * teeth + 1)
+    top = np.stack([xs, np.where(np.arange(xs.size) % 2 == 0, 1.4, 0.9)], axis=1)
+    comb = np.concatenate([np.array([[0.8, 0.6], [3.2, 0.6]]), top[:-1]])          # counter-clockwise
+    with g:
+        g.set_bodies([comb]); o.set_bodies([comb])
+        g.initializeData()
+        g.iblank_update()
+        n = o.update_ib()
+        assert n > 0
+        assert np.array_equal(g.get("celltype"), o.get("celltype"))
+        a, b = g.ghost_cells(), o.ghost_cells()
+        for k in ("cell", "stencil", "weights", "bi", "ip"):
+            assert np.array_equal(a[k], b[k]), k
+    o.close()
+
+
 def test_reference_mode_rejects_full_only_calls(ref_case):
     inp = ifx.make_input(50, 50, 1e-3, 150.0)
     with ifx.ImmerseFlow(inp, ref_case["xf"], ref_case["yf"]) as s:
