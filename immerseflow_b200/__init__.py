@@ -18,7 +18,8 @@ from typing import Optional, Sequence
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libimmerseflow_b200.so")
+# IFX_LIBRARY: explicit path of a build of the same C-ABI (kernel experiments, tools/build_variant.sh)
+LIB_PATH = os.environ.get("IFX_LIBRARY") or os.path.join(_HERE, "libimmerseflow_b200.so")
 
 IFX_ABI_VERSION = 1
 IFX_COMPAT_REFERENCE, IFX_COMPAT_FULL = 0, 1
