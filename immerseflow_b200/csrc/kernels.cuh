@@ -69,6 +69,28 @@ struct PpeSweepArgs {
 // partials in a fixed order and takes the stop decision on the device.  Deterministic: the
 // order depends only on the launch geometry, never on scheduling.
 // ---------------------------------------------------------------------------------------------
+// global residual over the slabs: every rank posts its partial into every rank's mailbox (NVLink P2P stores),
+// then adds all of them in rank order — same operands, same order, same stop decision everywhere.  One thread of
+// one CTA per launch runs this: kept out of line so that it does not set the register count of the sweep kernels.
+static __device__ __noinline__ void slab_combine_residual(const HaloCtx& hx, double& a, double& b) {
+  const unsigned slot = hx.mseq & (IFX_MAIL_SLOTS - 1);
+  const unsigned me = (unsigned)hx.rank;
+  for (int r = 0; r < hx.nranks; ++r) {
+    double* m = hx.mail[r] + ((size_t)slot * IFX_MAX_RANKS + me) * 2;
+    m[0] = a; m[1] = b;
+  }
+  __threadfence_system();
+  for (int r = 0; r < hx.nranks; ++r) st_release_sys(hx.mail_seq[r] + slot * IFX_MAX_RANKS + me, hx.mseq);
+  double ga = 0.0, gb = 0.0;
+  for (int r = 0; r < hx.nranks; ++r) {
+    const unsigned* q = hx.mail_seq[me] + slot * IFX_MAX_RANKS + r;
+    while (ld_acquire_sys(q) != hx.mseq) { __nanosleep(64); }
+    const volatile double* m = hx.mail[me] + ((size_t)slot * IFX_MAX_RANKS + r) * 2;
+    ga += m[0]; gb += m[1];
+  }
+  a = ga; b = gb;
+}
+
 template <int THREADS>
 __device__ __forceinline__ void block_reduce_and_decide(double r0, double r1, double* partials,
                                                         LoopCtl* ctl, const ReduceCfg& rc,
@@ -108,26 +130,7 @@ __device__ __forceinline__ void block_reduce_and_decide(double r0, double r1, do
     a = sh[0][0]; b = sh[1][0];
 #pragma unroll
     for (int w = 1; w < NW; ++w) { a += sh[0][w]; b += sh[1][w]; }
-    if (hx && hx->nranks > 1) {
-      // global residual over the slabs: every rank posts its partial into every rank's mailbox (NVLink P2P
-      // stores), then adds all of them in rank order — same operands, same order, same stop decision everywhere
-      const unsigned slot = hx->mseq & (IFX_MAIL_SLOTS - 1);
-      const unsigned me = (unsigned)hx->rank;
-      for (int r = 0; r < hx->nranks; ++r) {
-        double* m = hx->mail[r] + ((size_t)slot * IFX_MAX_RANKS + me) * 2;
-        m[0] = a; m[1] = b;
-      }
-      __threadfence_system();
-      for (int r = 0; r < hx->nranks; ++r) st_release_sys(hx->mail_seq[r] + slot * IFX_MAX_RANKS + me, hx->mseq);
-      double ga = 0.0, gb = 0.0;
-      for (int r = 0; r < hx->nranks; ++r) {
-        const unsigned* q = hx->mail_seq[me] + slot * IFX_MAX_RANKS + r;
-        while (ld_acquire_sys(q) != hx->mseq) { __nanosleep(64); }
-        const volatile double* m = hx->mail[me] + ((size_t)slot * IFX_MAX_RANKS + r) * 2;
-        ga += m[0]; gb += m[1];
-      }
-      a = ga; b = gb;
-    }
+    if (hx && hx->nranks > 1) slab_combine_residual(*hx, a, b);
     ctl->ticket = 0;
     ctl->res0 = a;
     ctl->res1 = b;
