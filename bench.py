@@ -56,7 +56,9 @@ def parse_args():
 
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    """SM clocks + throttle reasons DURING the timed region (B200_PROFILING.md's clocks line), read through NVML
+    from a sampling thread every 10 ms (the solver calls release the GIL); `nvidia-smi -lms` takes longer to start
+    than a short multi-GPU timed region lasts, so it is only the fallback."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -64,8 +66,52 @@ class ClockSampler:
         self.gpu = gpu_index
         self.proc = None
         self.path = None
+        self.nvml = None
+        self.handle = None
+        self.thread = None
+        self.stop_flag = False
+        self.sm, self.reasons, self.mx = [], set(), None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = None
+            try:
+                import torch
+                pr = torch.cuda.get_device_properties(gpu_index)
+                bus = "%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+                h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+            except Exception:
+                h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.nvml, self.handle = pynvml, h
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nvml = None
+
+    def _sample(self):
+        n = self.nvml
+        try:
+            self.sm.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+            r = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle) if hasattr(n, "nvmlDeviceGetCurrentClocksEventReasons") \
+                else n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+            for name, bit in (("hw_slowdown", 0x8), ("sw_power_cap", 0x4), ("sw_thermal_slowdown", 0x20),
+                              ("hw_thermal_slowdown", 0x40)):
+                if r & bit:
+                    self.reasons.add(name)
+        except Exception:
+            pass
+
+    def _loop(self):
+        while not self.stop_flag:
+            self._sample()
+            time.sleep(0.01)
 
     def start(self):
+        if self.nvml:
+            import threading
+            self.stop_flag = False
+            self.thread = threading.Thread(target=self._loop, daemon=True)
+            self.thread.start()
+            return
         try:
             f = tempfile.NamedTemporaryFile(prefix="ifx_clocks_", suffix=".csv", delete=False)
             self.path = f.name
@@ -76,6 +122,15 @@ class ClockSampler:
 
     def stop(self) -> dict:
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.nvml:
+            self.stop_flag = True
+            if self.thread:
+                self.thread.join(timeout=2)
+            if self.sm:
+                s = sorted(self.sm)
+                out.update(sm_mhz=float(np.median(s[len(s) // 2:])), sm_max_mhz=self.mx, samples=len(s), source="nvml")
+            out["reasons"] = sorted(self.reasons)
+            return out
         if not self.proc:
             return out
         self.proc.terminate()
@@ -105,6 +160,7 @@ class ClockSampler:
             out["sm_mhz"] = float(np.median(s[len(s) // 2:]))
             out["sm_max_mhz"] = max(mx)
             out["samples"] = len(sm)
+            out["source"] = "nvidia-smi"
         out["reasons"] = sorted(reasons)
         return out
 

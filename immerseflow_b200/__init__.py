@@ -13,7 +13,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 from dataclasses import dataclass
-from typing import Optional, Sequence
+from typing import Optional, Sequence, Tuple
 
 import numpy as np
 
@@ -34,6 +34,7 @@ C_ABI_SYMBOLS = [
     "ifx_read_input_file", "ifx_read_grid_file", "ifx_write_results_to_file",
     "ifx_create", "ifx_destroy", "ifx_initialize",
     "ifx_field_size", "ifx_set_field", "ifx_get_field", "ifx_save_field",
+    "ifx_checkpoint_write", "ifx_checkpoint_read",
     "ifx_ad_solve", "ifx_ppe_solve", "ifx_correct", "ifx_step", "ifx_reduce_sum", "ifx_get_residual_history",
     "ifx_set_bodies", "ifx_iblank_update", "ifx_ghost_cell_count", "ifx_get_ghost_cells",
     "ifx_ipc_export", "ifx_ipc_connect",
@@ -109,6 +110,8 @@ def load_library() -> C.CDLL:
     lib.ifx_set_field.argtypes = [vp, C.c_int, dp, C.c_size_t]
     lib.ifx_get_field.argtypes = [vp, C.c_int, dp, C.c_size_t]
     lib.ifx_save_field.argtypes = [vp, C.c_int, C.c_char_p]
+    lib.ifx_checkpoint_write.argtypes = [vp, C.c_char_p, C.c_longlong, C.c_double]
+    lib.ifx_checkpoint_read.argtypes = [vp, C.c_char_p, C.POINTER(C.c_longlong), C.POINTER(C.c_double)]
     for name in ("ifx_ad_solve", "ifx_ppe_solve", "ifx_correct", "ifx_step", "ifx_iblank_update"):
         getattr(lib, name).argtypes = [vp, C.POINTER(IfxStepStats)]
     lib.ifx_reduce_sum.argtypes = [vp, dp, C.c_size_t, dp]
@@ -305,6 +308,17 @@ class ImmerseFlow:
         self._check(self.lib.ifx_save_field(self._h, FIELD[field], os.fsencode(filename)), "ifx_save_field")
 
     # ---- immersed boundary --------------------------------------------------------------------
+    def save_checkpoint(self, path: str, step: int = 0, time: float = 0.0) -> None:
+        """Restart file: raw fp64 of u, v, p (+ uf, vf in full mode), see include/immerseflow_c.h."""
+        self._check(self.lib.ifx_checkpoint_write(self._h, os.fsencode(path), C.c_longlong(step), C.c_double(time)),
+                    "ifx_checkpoint_write")
+
+    def load_checkpoint(self, path: str) -> Tuple[int, float]:
+        step, time = C.c_longlong(0), C.c_double(0.0)
+        self._check(self.lib.ifx_checkpoint_read(self._h, os.fsencode(path), C.byref(step), C.byref(time)),
+                    "ifx_checkpoint_read")
+        return int(step.value), float(time.value)
+
     def set_bodies(self, bodies: Sequence[np.ndarray], velocities: Optional[Sequence[Sequence[float]]] = None) -> None:
         offs = np.zeros(len(bodies) + 1, dtype=np.int32)
         for b, m in enumerate(bodies):

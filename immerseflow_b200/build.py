@@ -26,6 +26,7 @@ STRICT = ["-fmad=false"]
 SOURCES = [
     ("capi.cu", True),
     ("capi_full.cu", True),
+    ("capi_ckpt.cu", True),
     ("kernels_ad.cu", True),
     ("kernels_ppe.cu", True),
     ("kernels_v4.cu", True),

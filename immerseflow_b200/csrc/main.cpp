@@ -36,6 +36,8 @@ struct Args {
   bool write_every_step = false;
   bool reference_log = false;
   bool exact = false;
+  bool checkpoints = false;      // write restart files every Write_Interval steps and after the last one
+  std::string restart;           // explicit restart file (default when Restart != 0: <results>/restart.<Restart_Time>.ifx)
   int device = 0;
 };
 
@@ -43,9 +45,12 @@ static void usage() {
   std::cout <<
       "immerseflow [--input FILE] [--xgrid FILE] [--ygrid FILE] [--stretched] [--results DIR]\n"
       "            [--mode reference|full] [--bodies FILE] [--steps N] [--write-every-step]\n"
-      "            [--reference-log] [--exact-reduction] [--device K]\n"
+      "            [--reference-log] [--exact-reduction] [--checkpoints] [--restart FILE] [--device K]\n"
       "  defaults reproduce the reference binary run from src/: ../inputs/inputs.txt, ../inputs/{x,y}grid.dat2,\n"
       "  tmax predictor steps, ../results/{final_results,uc,vc}.dat.  --stretched picks ../inputs/{x,y}grid.dat.\n"
+      "  inputs.txt `Write Interval` N: results are (re)written every N steps as well as after the last one; with\n"
+      "  --checkpoints a restart file <results>/restart.<step, 7 digits>.ifx goes with them.  `Restart 1 T` in inputs.txt\n"
+      "  (or --restart FILE) continues from <results>/restart.<T>.ifx: steps T+1 .. tmax, bit-identical to an unbroken run.\n"
       "  --bodies FILE (full mode): `nbodies`, then per body `nmarkers ub vb` and nmarkers lines `x y` (counter-clockwise).\n";
 }
 
@@ -65,6 +70,8 @@ static Args parse(int argc, char** argv) {
     else if (o == "--write-every-step") a.write_every_step = true;
     else if (o == "--reference-log") a.reference_log = true;
     else if (o == "--exact-reduction") a.exact = true;
+    else if (o == "--checkpoints") a.checkpoints = true;
+    else if (o == "--restart") a.restart = val();
     else if (o == "--device") a.device = std::atoi(val().c_str());
     else if (o == "-h" || o == "--help") { usage(); std::exit(0); }
     else die("unknown option " + o);
@@ -121,8 +128,22 @@ int main(int argc, char** argv) {
   check(s, ifx_save_field(s, IFX_FIELD_IBLANK, (a.results + "/final_results.dat").c_str()), "final_results.dat");   // preSim.cu:217
 
   const long nsteps = a.steps >= 0 ? a.steps : (long)in.tmax;        // tmax is a step COUNT in the reference (main.cu:93)
+  auto ckpt_name = [&](long step) {
+    char b[32];
+    std::snprintf(b, sizeof(b), "/restart.%07ld.ifx", step);
+    return a.results + b;
+  };
+  // Restart / Restart_Time (main.cu:27-30; read and ignored by the reference): continue from a restart file
+  long first = 0;
+  if (in.Restart != 0 || !a.restart.empty()) {
+    const std::string f = a.restart.empty() ? ckpt_name(in.Restart_Time) : a.restart;
+    long long st = 0; double t = 0.0;
+    check(s, ifx_checkpoint_read(s, f.c_str(), &st, &t), "ifx_checkpoint_read");
+    first = (long)st;
+    std::printf("restarted from %s: step %ld, t = %g\n", f.c_str(), first, t);
+  }
   std::vector<double> hist(2 * 64);
-  for (long step = 0; step < nsteps; step++) {
+  for (long step = first; step < nsteps; step++) {
     ifx_step_stats st;
     check(s, ifx_step(s, &st), "ifx_step");
     if (a.reference_log) {                                           // the reference's own lines, ADSolver.cu:274,313,369
@@ -135,7 +156,10 @@ int main(int argc, char** argv) {
     } else {
       std::printf("step %ld: predictor %d iterations (%.3e, %.3e), %.3f ms\n", step + 1, st.ad_iters, st.ad_ures, st.ad_vres, st.ms_total);
     }
-    if (a.write_every_step || step == nsteps - 1) {
+    const bool interval = in.Write_Interval > 0 && (step + 1) % in.Write_Interval == 0;     // main.cu:47-50
+    if (a.checkpoints && (interval || step == nsteps - 1))
+      check(s, ifx_checkpoint_write(s, ckpt_name(step + 1).c_str(), step + 1, (step + 1) * in.dt), "ifx_checkpoint_write");
+    if (a.write_every_step || interval || step == nsteps - 1) {
       check(s, ifx_save_field(s, IFX_FIELD_U, (a.results + "/uc.dat").c_str()), "uc.dat");       // ADSolver.cu:378
       check(s, ifx_save_field(s, IFX_FIELD_V, (a.results + "/vc.dat").c_str()), "vc.dat");       // ADSolver.cu:379
       if (a.mode == "full") check(s, ifx_save_field(s, IFX_FIELD_P, (a.results + "/p.dat").c_str()), "p.dat");   // PPESolver.cu:197

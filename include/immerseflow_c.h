@@ -153,6 +153,12 @@ int ifx_set_field(ifx_solver* s, ifx_field f, const double* host, size_t n);
 int ifx_get_field(ifx_solver* s, ifx_field f, double* host, size_t n);
 /* replaces saveDataToFile(), postSim.cu:10-39: D2H + Tecplot ASCII */
 int ifx_save_field(ifx_solver* s, ifx_field f, const char* filename);
+/* Restart files: what `Restart` / `Restart_Time` / `Write_Interval` of inputs.txt ask for (parsed at
+ * main.cu:27-30,47-50, never used by the reference; predecessor: test/UTIL_PRE_SIM.f90:120-150).  Raw fp64 of
+ * u, v, p (+ uf, vf in IFX_COMPAT_FULL); a run continued from a file is bit-identical to an uninterrupted one.
+ * Slab handles write / read their own rows (one file per rank). */
+int ifx_checkpoint_write(ifx_solver* s, const char* path, long long step, double time);
+int ifx_checkpoint_read(ifx_solver* s, const char* path, long long* step, double* time);
 
 /* ---- the hot path ------------------------------------------------------------------------- */
 /* replaces ImmerseFlow::ADsolver(), src/include/ADSolver.cu:268-395 (one predictor step; no file I/O) */

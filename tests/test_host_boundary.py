@@ -89,6 +89,44 @@ def test_tecplot_writer_bytes_match_reference_file(ref_case, tmp_path):
         ifx.write_results_to_file(g.xc, g.yc, data, g.nx, g.ny, str(tmp_path / "no_dir" / "x.dat"))
 
 
+def test_tecplot_writer_matches_printf_on_adversarial_values(tmp_path, monkeypatch):
+    """The writer formats "%f" itself (one FMA gives the exact product v*1e6) on every host thread.  It must print
+    what printf prints: exact ties at the sixth decimal (k/2^m values such as 1/128), negative zero, values that
+    round to zero, large magnitudes, inf/nan, and the row/thread chunking must not reorder anything."""
+    rng = np.random.default_rng(7)
+    ties = np.array([(2 * n + 1) * 15625 / 2.0 ** m for n in range(40) for m in (7, 8, 10, 13)])      # exact .5 at 1e-6
+    near = np.concatenate([np.nextafter(ties, np.inf), np.nextafter(ties, -np.inf)])
+    special = np.array([0.0, -0.0, 1e-7, -1e-7, 4.9999995e-7, 5e-7, -5e-7, 0.9999995, 0.99999949999, 123456789.1234565,
+                        3.9999e9, 4.0e9, 1e15, -2.5e18, 1e300, np.inf, -np.inf, np.nan, 2.0 ** -1074, 100.0, 1.0000005])
+    vals = np.concatenate([ties, -ties, near, special, rng.standard_normal(3000) * 10.0 ** rng.integers(-8, 9, 3000)])
+    ni = 37
+    nj = (vals.size + ni - 1) // ni
+    data = np.resize(vals, ni * nj)
+    x = rng.standard_normal(ni) * 3.0
+    y = np.concatenate([[-0.0, 1 / 128], rng.standard_normal(nj - 2)])
+    want = ['TITLE = "Post Processing Tecplot"', 'VARIABLES = "X","Y","T"',
+            f'ZONE T="BIG ZONE", I={ni}, J={nj}, DATAPACKING=POINT']
+    want += ["%f,%f,%f" % (x[i], y[j], data[i + j * ni]) for j in range(nj) for i in range(ni)]
+    for threads in ("1", "3", "16"):
+        monkeypatch.setenv("IFX_IO_THREADS", threads)
+        out = tmp_path / f"adv_{threads}.dat"
+        ifx.write_results_to_file(x, y, data, ni, nj, str(out))
+        got = out.read_text().split("\n")
+        assert got[-1] == "" and got[:-1] == want, threads
+
+
+def test_tecplot_writer_many_rows_in_order(tmp_path):
+    ni, nj = 257, 1500                       # several batches of row chunks
+    x = np.linspace(-1.0, 2.0, ni); y = np.linspace(0.0, 5.0, nj)
+    data = np.arange(ni * nj, dtype=np.float64) * 0.001
+    out = tmp_path / "rows.dat"
+    ifx.write_results_to_file(x, y, data, ni, nj, str(out))
+    lines = out.read_text().split("\n")
+    assert len(lines) == 3 + ni * nj + 1
+    for k in (0, 1, ni - 1, ni, 12345, ni * nj - 1):
+        assert lines[3 + k] == "%f,%f,%f" % (x[k % ni], y[k // ni], data[k])
+
+
 def test_create_without_gpu_fails_loudly(ref_case):
     """No silent CPU path: on a box without a CUDA device the solver refuses to exist."""
     lib = ifx.load_library()
