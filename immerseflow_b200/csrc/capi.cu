@@ -312,6 +312,14 @@ extern "C" int ifx_create(const ifx_input* in, const double* xf, const double* y
   if (opt.j_begin < 1 || opt.j_end > in->ny - 1 || opt.j_begin >= opt.j_end)
     return fail(nullptr, IFX_ERR_INVALID, "bad slab rows");
   if (opt.sweeps_per_batch < 1) opt.sweeps_per_batch = 64;
+  if (opt.ppe_solver == 0) opt.ppe_solver = (in->PPE_solver == 3) ? 3 : 1;      // 0 / 1 / 2 in the file: point Jacobi
+  if (opt.ppe_omega == 0.0) opt.ppe_omega = (in->w_PPE != 0) ? (double)in->w_PPE : 1.0;
+  if (opt.ppe_solver != 1 && opt.ppe_solver != 3)
+    return fail(nullptr, IFX_ERR_INVALID, "ppe_solver: 1 (point Jacobi) or 3 (red-black SOR); line SOR is not built");
+  if (opt.ppe_solver == 3 && opt.compat != IFX_COMPAT_FULL)
+    return fail(nullptr, IFX_ERR_INVALID, "red-black SOR needs IFX_COMPAT_FULL (the reference mode reproduces the reference's Jacobi)");
+  if (opt.ppe_solver == 3 && !(opt.ppe_omega > 0.0 && opt.ppe_omega < 2.0))
+    return fail(nullptr, IFX_ERR_INVALID, "SOR needs 0 < ppe_omega < 2");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
     cudaGetLastError();
@@ -807,11 +815,26 @@ int ifx::run_ppe_loop(ifx_solver* s, ifx_step_stats* st, bool laplace_ref) {
     pa.rc.decide = exact ? 0 : 1;
     pa.rc.certify = (exact || slabs) ? 0 : 1;
     pa.rc.band = rounding_band(s, nblocks, ry);
+    // red-black SOR: iteration m = colour-0 half-sweep base -> partner (it also evaluates the
+    // residual of iterate m-1 and takes the stop decision, like a Jacobi sweep) + colour-1 half-sweep partner -> base.
+    // The iterate always ends up in the buffer it started in.
+    const bool sor = !laplace_ref && s->opt.ppe_solver == 3;
+    pa.sor = sor ? 1 : 0; pa.sor_omega = s->opt.ppe_omega;
+    const int decide = pa.rc.decide;
     auto set_sweep = [&](int m) {     // sweep m: iterate m-1 -> iterate m, evaluates residual(iterate m-1)
-      const int src = (base + m - 1) & 1;
+      const int src = sor ? base : (base + m - 1) & 1;
       pa.pC = s->p[src]; pa.pT = s->p[src ^ 1];
       pa.rc.eval_iter = m - 1;
+      pa.rc.decide = decide;
+      pa.sor_colour = 0;
       const int fo[1] = {4 + (src ^ 1)};
+      make_halo_ctx(s, 1, 1, fo, &pa.hx);
+    };
+    auto set_black = [&]() {          // second half of a SOR iteration: no residual bookkeeping
+      pa.pC = s->p[base ^ 1]; pa.pT = s->p[base];
+      pa.rc.eval_iter = 0; pa.rc.decide = 0;
+      pa.sor_colour = 1;
+      const int fo[1] = {4 + base};
       make_halo_ctx(s, 1, 1, fo, &pa.hx);
     };
     int m = 0;
@@ -822,6 +845,10 @@ int ifx::run_ppe_loop(ifx_solver* s, ifx_step_stats* st, bool laplace_ref) {
         pa.force = 0;
         if ((rc = launch_ppe_sweep(s, pa, grid, laplace_ref, exact)) != IFX_OK) return rc;
         if (exact && m > 1 && (rc = exact_decide(s, pa.rc, false)) != IFX_OK) return rc;
+        if (sor) {
+          set_black();
+          if ((rc = launch_ppe_sweep(s, pa, grid, laplace_ref, false)) != IFX_OK) return rc;
+        }
       }
       if ((rc = fetch_ctl(s)) != IFX_OK) return rc;
       if (s->h_ctl->done && s->h_ctl->ambiguous && !slabs) {
@@ -835,13 +862,18 @@ int ifx::run_ppe_loop(ifx_solver* s, ifx_step_stats* st, bool laplace_ref) {
         if ((rc = exact_decide(s, pa.rc, false)) != IFX_OK) return rc;
         pa.rc.decide = 1;
         if ((rc = fetch_ctl(s)) != IFX_OK) return rc;
+        if (sor && !s->h_ctl->done) {    // not converged after all: the iteration's second half was skipped, run it
+          set_black();
+          pa.force = 0;
+          if ((rc = launch_ppe_sweep(s, pa, grid, laplace_ref, false)) != IFX_OK) return rc;
+        }
       }
       if (s->h_ctl->done) break;
       if (m >= itermax + 1) return fail(s, IFX_ERR_STATE, "Poisson loop ran past PPE_itermax without a decision");
     }
     K = s->h_ctl->iter;
-    s->cur_p = (base + K) & 1;
-    if (slabs && (rc = halo_wait(s, 1, seq_before + (unsigned)K, tw_ppe)) != IFX_OK) return rc;
+    s->cur_p = sor ? base : (base + K) & 1;
+    if (slabs && (rc = halo_wait(s, 1, seq_before + (unsigned)(sor ? 2 * K : K), tw_ppe)) != IFX_OK) return rc;
   }
   if (laplace_ref) {   // PPESolver.cu:195
     s->launches++;

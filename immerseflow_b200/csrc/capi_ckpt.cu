@@ -62,6 +62,12 @@ extern "C" int ifx_checkpoint_read(ifx_solver* s, const char* path, long long* s
   if (h.compat != s->opt.compat) return bad("written in the other compat mode");
   const int want = s->opt.compat == IFX_COMPAT_FULL ? 5 : 3;
   if (h.nfields != want) return bad("unexpected field count");
+  // bodies set but not classified yet: classify first — ifx_iblank_update invalidates the face velocities (closed
+  // faces move with the bodies), which must not happen after the file's faces have been put in place
+  if (s->bodies_dirty) {
+    const int rc = ifx_iblank_update(s, nullptr);
+    if (rc != IFX_OK) { std::fclose(fp); return rc; }
+  }
   std::vector<double> buf;
   for (int k = 0; k < h.nfields; k++) {      // order in the file: u, v, p, then uf, vf (faces after cells: ifx_set_field
     int id; unsigned long long n;            // invalidates the faces when cell velocities are set)

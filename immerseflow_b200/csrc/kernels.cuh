@@ -60,6 +60,8 @@ struct PpeSweepArgs {
   ReduceCfg rc;
   int rows_per_cta;
   int force;
+  int sor, sor_colour;                // red-black SOR half-sweep of the given colour instead of a Jacobi sweep
+  double sor_omega;
   HaloCtx hx;
 };
 

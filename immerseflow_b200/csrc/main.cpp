@@ -37,6 +37,8 @@ struct Args {
   bool reference_log = false;
   bool exact = false;
   bool checkpoints = false;      // write restart files every Write_Interval steps and after the last one
+  int ppe_solver = 0;            // 0: PPE_Solver of inputs.txt; 1 point Jacobi; 3 red-black SOR (full mode)
+  double ppe_omega = 0.0;        // 0: w-PPE of inputs.txt (an integer there)
   std::string restart;           // explicit restart file (default when Restart != 0: <results>/restart.<Restart_Time>.ifx)
   int device = 0;
 };
@@ -46,11 +48,13 @@ static void usage() {
       "immerseflow [--input FILE] [--xgrid FILE] [--ygrid FILE] [--stretched] [--results DIR]\n"
       "            [--mode reference|full] [--bodies FILE] [--steps N] [--write-every-step]\n"
       "            [--reference-log] [--exact-reduction] [--checkpoints] [--restart FILE] [--device K]\n"
+      "            [--ppe-solver 1|3] [--ppe-omega W]\n"
       "  defaults reproduce the reference binary run from src/: ../inputs/inputs.txt, ../inputs/{x,y}grid.dat2,\n"
       "  tmax predictor steps, ../results/{final_results,uc,vc}.dat.  --stretched picks ../inputs/{x,y}grid.dat.\n"
       "  inputs.txt `Write Interval` N: results are (re)written every N steps as well as after the last one; with\n"
       "  --checkpoints a restart file <results>/restart.<step, 7 digits>.ifx goes with them.  `Restart 1 T` in inputs.txt\n"
       "  (or --restart FILE) continues from <results>/restart.<T>.ifx: steps T+1 .. tmax, bit-identical to an unbroken run.\n"
+      "  --ppe-solver 3 (or PPE_Solver 3 in inputs.txt; full mode): red-black SOR with factor --ppe-omega / w-PPE.\n"
       "  --bodies FILE (full mode): `nbodies`, then per body `nmarkers ub vb` and nmarkers lines `x y` (counter-clockwise).\n";
 }
 
@@ -71,6 +75,8 @@ static Args parse(int argc, char** argv) {
     else if (o == "--reference-log") a.reference_log = true;
     else if (o == "--exact-reduction") a.exact = true;
     else if (o == "--checkpoints") a.checkpoints = true;
+    else if (o == "--ppe-solver") a.ppe_solver = std::atoi(val().c_str());
+    else if (o == "--ppe-omega") a.ppe_omega = std::atof(val().c_str());
     else if (o == "--restart") a.restart = val();
     else if (o == "--device") a.device = std::atoi(val().c_str());
     else if (o == "-h" || o == "--help") { usage(); std::exit(0); }
@@ -100,6 +106,8 @@ int main(int argc, char** argv) {
   opt.compat = (a.mode == "full") ? IFX_COMPAT_FULL : IFX_COMPAT_REFERENCE;
   opt.reduce_mode = a.exact ? IFX_REDUCE_REFERENCE : IFX_REDUCE_FUSED;
   opt.ppe_abs_residual = (a.mode == "full") ? 1 : 0;
+  opt.ppe_solver = (a.mode == "full") ? a.ppe_solver : 1;       // PPE_Solver / w-PPE (main.cu:42): full mode only
+  opt.ppe_omega = a.ppe_omega;
   ifx_solver* s = nullptr;
   if (ifx_create(&in, xf.data(), yf.data(), &opt, &s) != IFX_OK) die(std::string("ImmerseFlow error in ifx_create: ") + ifx_last_error(nullptr));
   std::printf("grid %d x %d cells (%d x %d with ghost cells), dt = %g, Re = %g, AD_itermax = %d, PPE_itermax = %d\n",

@@ -91,7 +91,12 @@ typedef struct {
   int j_begin, j_end;
   int sweeps_per_batch;     /* Poisson sweeps enqueued between host looks at the stop flag */
   int use_graphs;           /* capture sweep batches in CUDA graphs */
-  int reserved[8];
+  /* Poisson iteration (IFX_COMPAT_FULL).  The reference documents PPE_Solver "1. Point GS, 2. Line
+   * SOR" and w-PPE in inputs.txt, parses them (main.cu:42) and always runs point Jacobi.  0 = take
+   * ifx_input.PPE_solver; 1 = point Jacobi (the reference's sweep); 3 = red-black SOR with factor ppe_omega. */
+  int ppe_solver;
+  double ppe_omega;         /* 0 = take ifx_input.w_PPE (an int in the reference's struct, globalVariables.cuh:26) */
+  int reserved[5];
 } ifx_options;
 
 /* Per-call statistics (replaces the reference's printf of "iter = %d %f %f", ADSolver.cu:369). */

@@ -143,6 +143,10 @@ void orc_full_set_bodies(orc_full* s, int nbodies, const int* off, const double*
 int orc_full_update_ib(orc_full* s);
 int orc_full_predictor(orc_full* s, double* stats);
 int orc_full_poisson(orc_full* s, double* stats);
+void orc_ppe_sor_halfsweep(int nx, int ny, const double* cP, const double* cxm, const double* cxp, const double* cym,
+                           const double* cyp, const unsigned char* celltype, const double* rhs, int colour, double omega,
+                           const double* p, double* p_new);
+void orc_full_set_ppe_solver(orc_full* s, int solver /* 1 Jacobi, 3 red-black SOR */, double omega);
 void orc_full_correct(orc_full* s);
 void orc_full_step(orc_full* s, double* stats);
 int orc_full_get(orc_full* s, int field, double* out);

@@ -324,6 +324,36 @@ void orc_ppe_sweep_general(int nx, int ny, const double* cP, const double* cxm, 
 }
 
 /* -----------------------------------------------------------------------------------------------
+ * SURVEY 8(f)-1 — red-black successive over-relaxation, the first of the "better Poisson iterations" the input
+ * file's PPE_Solver / w-PPE fields ask for (parsed at main.cu:42, unused by the reference).  UNPINNED.
+ * One half-sweep: cells of one colour ((i + j + colour) even) move to  p + omega ((rhs - t)/cP - p)  with t and
+ * the closed-face substitutions exactly as in the Jacobi sweep above; everything else is copied.  An iteration
+ * is the colour-0 half-sweep followed by the colour-1 half-sweep on its result.
+ * --------------------------------------------------------------------------------------------- */
+void orc_ppe_sor_halfsweep(int nx, int ny, const double* cP, const double* cxm, const double* cxp, const double* cym,
+                           const double* cyp, const unsigned char* celltype, const double* rhs, int colour, double omega,
+                           const double* p, double* p_new) {
+#pragma omp parallel for
+  for (int id = 0; id < nx * ny; id++) {
+    const int i = id % nx, j = id / nx;
+    if (!(i > 0 && i < nx - 1 && j > 0 && j < ny - 1)) continue;
+    const double pc = p[id];
+    p_new[id] = pc;
+    if (!IS_FLUID(celltype[id]) || ((i + j + colour) & 1)) continue;
+    const double pw = (i == 1 || !IS_FLUID(celltype[id - 1])) ? pc : p[id - 1];
+    const double pe = (i == nx - 2 || !IS_FLUID(celltype[id + 1])) ? pc : p[id + 1];
+    const double ps = (j == 1 || !IS_FLUID(celltype[id - nx])) ? pc : p[id - nx];
+    const double pn = (j == ny - 2 || !IS_FLUID(celltype[id + nx])) ? pc : p[id + nx];
+    double t = pw * cxm[id];
+    t = fma(pe, cxp[id], t);
+    t = fma(pn, cyp[id], t);
+    t = fma(ps, cym[id], t);
+    const double pj = (rhs[id] - t) / cP[id];
+    p_new[id] = pc + omega * (pj - pc);
+  }
+}
+
+/* -----------------------------------------------------------------------------------------------
  * a18 — projection.  With PN(nb) = p of the neighbour, or the cell's own p when the neighbour is a ring cell or
  * not fluid (zero normal gradient), on fluid cells
  *   u = u* - dt (pe - pw)/dx_i,  pe = rcp(dx_i+dx_ip1) * fma(PN(E), dx_i, p_C*dx_ip1)   (face value, velf form)
@@ -407,6 +437,8 @@ struct orc_full {
   int nbodies; int* off; double *xm, *ym, *ub, *vb;
   int ngc, *cell, *stencil, *body; double *wd, *wn, *bi, *ip;
   int faces_valid;
+  int ppe_solver;                     /* 1: point Jacobi (the reference's sweep), 3: red-black SOR */
+  double w_ppe;
 };
 
 orc_full* orc_full_create(int nx, int ny, const double* xf, const double* yf, double dt, double Re, int AD_itermax,
@@ -415,6 +447,7 @@ orc_full* orc_full_create(int nx, int ny, const double* xf, const double* yf, do
   const size_t N = (size_t)nx * ny;
   s->nx = nx; s->ny = ny; s->dt = dt; s->Re = Re; s->AD_itermax = AD_itermax; s->PPE_itermax = PPE_itermax;
   s->ad_tol = ad_tol; s->ppe_tol = ppe_tol; s->ppe_abs = ppe_abs;
+  s->ppe_solver = 1; s->w_ppe = 1.0;
   for (int q = 0; q < 4; q++) { s->two_bc_u[q] = bc_u[q] * 2.0; s->two_bc_v[q] = bc_v[q] * 2.0; }   /* W, E, S, N */
   s->xc = (double*)calloc(nx, 8); s->yc = (double*)calloc(ny, 8);
   s->dx = (double*)calloc(N, 8); s->dy = (double*)calloc(N, 8);
@@ -556,8 +589,13 @@ int orc_full_poisson(orc_full* s, double* stats) {
   double R = 1.0, Rabs = 1.0;
   int iter = 0;
   while ((s->ppe_abs ? Rabs : R) > s->ppe_tol && iter < s->PPE_itermax) {
-    orc_ppe_sweep_general(nx, ny, cP, cxm, cxp, cym, cyp, s->celltype, s->rhs, pc, pT, NULL);
-    double* t = pc; pc = pT; pT = t;
+    if (s->ppe_solver == 3) {       /* red-black SOR: two half-sweeps, the iterate ends up where it started */
+      orc_ppe_sor_halfsweep(nx, ny, cP, cxm, cxp, cym, cyp, s->celltype, s->rhs, 0, s->w_ppe, pc, pT);
+      orc_ppe_sor_halfsweep(nx, ny, cP, cxm, cxp, cym, cyp, s->celltype, s->rhs, 1, s->w_ppe, pT, pc);
+    } else {
+      orc_ppe_sweep_general(nx, ny, cP, cxm, cxp, cym, cyp, s->celltype, s->rhs, pc, pT, NULL);
+      double* t = pc; pc = pT; pT = t;
+    }
     /* residual of the new iterate (the reference evaluates it in a second kernel too, PPESolver.cu:182);
      * `scratch` only absorbs the sweep's p_new output */
     orc_ppe_sweep_general(nx, ny, cP, cxm, cxp, cym, cyp, s->celltype, s->rhs, pc, scratch, res);
@@ -573,6 +611,8 @@ int orc_full_poisson(orc_full* s, double* stats) {
   free(mem);
   return iter;
 }
+
+void orc_full_set_ppe_solver(orc_full* s, int solver, double omega) { s->ppe_solver = solver; s->w_ppe = omega; }
 
 void orc_full_correct(orc_full* s) {
   const size_t N = (size_t)s->nx * s->ny;

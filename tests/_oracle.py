@@ -171,6 +171,10 @@ class FullSolver:
         a = np.ascontiguousarray(a, dtype=np.float64).reshape(-1)
         assert lib().orc_full_set(self.h, FIELD[name], P(a)) == 0
 
+    def set_ppe_solver(self, solver, omega):
+        lib().orc_full_set_ppe_solver.argtypes = [C.c_void_p, C.c_int, C.c_double]
+        lib().orc_full_set_ppe_solver(self.h, int(solver), float(omega))
+
     def predictor(self):
         lib().orc_full_predictor(self.h, P(self.stats)); return self.stats.copy()
 

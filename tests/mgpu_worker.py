@@ -77,7 +77,7 @@ def run_case(compat, ncx, ncy, steps, ppe_it, bc=None, stretched=True):
     return ok
 
 
-def run_bodies_case(ncx, ncy, steps, moving):
+def run_bodies_case(ncx, ncy, steps, moving, ppe_solver=1, ppe_omega=1.0):
     """Immersed bodies straddling the slab boundaries (configs 3-5 of BASELINE.json in miniature): cell types,
     ghost-cell maps and weights, u, v, p and the iteration counts of the slab run against the single-GPU run AND the
     CPU oracle, bit for bit."""
@@ -87,7 +87,7 @@ def run_bodies_case(ncx, ncy, steps, moving):
     dt, Re, ad_it, ppe_it = 2e-3, 200.0, 15, 60
     inp = ifx.make_input(ncx, ncy, dt, Re, AD_itermax=ad_it, PPE_itermax=ppe_it)
     nx, ny = inp.nx, inp.ny
-    kw = dict(compat=ifx.IFX_COMPAT_FULL, ppe_abs_residual=1)
+    kw = dict(compat=ifx.IFX_COMPAT_FULL, ppe_abs_residual=1, ppe_solver=ppe_solver, ppe_omega=ppe_omega)
 
     def bodies_at(step):
         sh = 0.013 * step if moving else 0.021      # off the grid's symmetry line: stencils cross the slab boundary
@@ -123,6 +123,7 @@ def run_bodies_case(ncx, ncy, steps, moving):
         ref.initializeData()
         ref.set("u", u0); ref.set("v", v0); ref.set("p", p0)
         o = orc.FullSolver(xf, yf, dt, Re, ad_it, ppe_it, ppe_abs=1)
+        o.set_ppe_solver(ppe_solver, ppe_omega)
         o.set("u", u0); o.set("v", v0)
         inner = np.zeros((ny, nx), bool); inner[1:-1, 1:-1] = True
         inner = inner.reshape(-1)
@@ -153,7 +154,7 @@ def run_bodies_case(ncx, ncy, steps, moving):
                 lo, hi = slabs.local_rows(ny, world, r)
                 if not np.array_equal(q["celltype"].reshape(-1, nx)[:, 1:-1], want_ct[lo:hi, 1:-1]):
                     msgs.append(f"rank {r}: stored cell types (halo rows included) differ from the single-GPU run")
-            print(f"[bodies moving={moving}] {ncx}x{ncy} world={world} step {step}: counts {counts}, "
+            print(f"[bodies moving={moving} solver={ppe_solver}] {ncx}x{ncy} world={world} step {step}: counts {counts}, "
                   f"{len(gc['cell'])} ghost cells ({[len(q['gc']['cell']) for q in parts]}): {'OK' if not msgs else msgs}")
             ok = ok and not msgs
         ref.close(); o.close()
@@ -169,6 +170,7 @@ def main():
     ok = run_case(ifx.IFX_COMPAT_FULL, 260, 130, 3, 40, bc={"u_bc_w": 0.0, "u_bc_e": 0.0, "u_bc_s": 0.0, "u_bc_n": 1.0}) and ok
     ok = run_bodies_case(257, 130, 3, moving=False) and ok
     ok = run_bodies_case(300, 161, 3, moving=True) and ok
+    ok = run_bodies_case(257, 130, 2, moving=False, ppe_solver=3, ppe_omega=1.8) and ok      # red-black SOR on slabs
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, 0)
     dist.destroy_process_group()

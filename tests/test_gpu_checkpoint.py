@@ -17,8 +17,9 @@ pytestmark = pytest.mark.gpu
 
 def _run(mode, tmp_path, split):
     full = mode == "full"
-    xf, yf = orc.stretched_faces(140, 4.0, 1.02), orc.stretched_faces(90, 2.0, 1.02)
-    inp = ifx.make_input(140, 90, 1e-3, 150.0, AD_itermax=12, PPE_itermax=40)
+    ncx, ncy = (140, 90) if full else (90, 140)        # reference mode needs nx <= ny (App. A Q2: vf == 0 there)
+    xf, yf = orc.stretched_faces(ncx, 4.0, 1.02), orc.stretched_faces(ncy, 2.0, 1.02)
+    inp = ifx.make_input(ncx, ncy, 1e-3, 150.0, AD_itermax=12, PPE_itermax=40)
     kw = dict(compat=ifx.IFX_COMPAT_FULL, ppe_abs_residual=1) if full else {}
     bodies = [orc.circle_markers(1.5, 1.0, 0.3, 48)]
 
