@@ -385,6 +385,8 @@ def main():
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_cell": 49, "ms_per_launch": ad_launch_ms,
                 "poisson": {"kernel": "k_sweep_v4<poisson %s>" % ("general" if full else "laplace"), "achieved": ach_ppe,
+                            "traffic": measured_traffic("k_sweep_v4_ppe_general" if full else "k_sweep_v4_ppe_laplace", ncx, ncy)
+                            if world == 1 else None,
                             "frac": ach_ppe / peak, "algorithmic_bytes_per_cell": ppe_b_cell, "ms_per_launch": ppe_launch_ms,
                             "sweeps_per_s": 1e3 / ppe_launch_ms},
                 "projection_ms": float(np.mean(cor_ms)), "iblank_ghost_cells_ms": float(np.mean(ib_ms)),

@@ -47,7 +47,7 @@ extern "C" void ifx_default_options(ifx_options* o) {
   o->rank = 0; o->nranks = 1;
   o->j_begin = 0; o->j_end = 0;        // 0,0 = whole grid
   o->sweeps_per_batch = 64;
-  o->use_graphs = 1;
+  o->use_graphs = 0;                   // reserved, ignored
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -90,7 +90,8 @@ typedef struct {
   int rank, nranks;
   int j_begin, j_end;
   int sweeps_per_batch;     /* Poisson sweeps enqueued between host looks at the stop flag */
-  int use_graphs;           /* capture sweep batches in CUDA graphs */
+  int use_graphs;           /* reserved (ignored): sweep batches are plain stream launches; a graph `while` node is
+                               DESIGN.md's next step for launch-bound small grids */
   /* Poisson iteration (IFX_COMPAT_FULL).  The reference documents PPE_Solver "1. Point GS, 2. Line
    * SOR" and w-PPE in inputs.txt, parses them (main.cu:42) and always runs point Jacobi.  0 = take
    * ifx_input.PPE_solver; 1 = point Jacobi (the reference's sweep); 3 = red-black SOR with factor ppe_omega. */
