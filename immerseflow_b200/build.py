@@ -35,6 +35,7 @@ SOURCES = [
     ("kernels_halo.cu", True),
     ("kernels_full.cu", True),
     ("kernels_ib.cu", True),
+    ("kernels_mg.cu", True),
     ("kernels_ic.cu", False),   # default flags on purpose: same libdevice expansion as the reference build
     ("io.cpp", True),
 ]

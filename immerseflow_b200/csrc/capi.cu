@@ -312,14 +312,20 @@ extern "C" int ifx_create(const ifx_input* in, const double* xf, const double* y
   if (opt.j_begin < 1 || opt.j_end > in->ny - 1 || opt.j_begin >= opt.j_end)
     return fail(nullptr, IFX_ERR_INVALID, "bad slab rows");
   if (opt.sweeps_per_batch < 1) opt.sweeps_per_batch = 64;
-  if (opt.ppe_solver == 0) opt.ppe_solver = (in->PPE_solver == 3) ? 3 : 1;      // 0 / 1 / 2 in the file: point Jacobi
+  if (opt.ppe_solver == 0) opt.ppe_solver = (in->PPE_solver == 3 || in->PPE_solver == 4) ? in->PPE_solver : 1;   // 0 / 1 / 2 in the file: point Jacobi
   if (opt.ppe_omega == 0.0) opt.ppe_omega = (in->w_PPE != 0) ? (double)in->w_PPE : 1.0;
-  if (opt.ppe_solver != 1 && opt.ppe_solver != 3)
-    return fail(nullptr, IFX_ERR_INVALID, "ppe_solver: 1 (point Jacobi) or 3 (red-black SOR); line SOR is not built");
-  if (opt.ppe_solver == 3 && opt.compat != IFX_COMPAT_FULL)
-    return fail(nullptr, IFX_ERR_INVALID, "red-black SOR needs IFX_COMPAT_FULL (the reference mode reproduces the reference's Jacobi)");
-  if (opt.ppe_solver == 3 && !(opt.ppe_omega > 0.0 && opt.ppe_omega < 2.0))
+  if (opt.ppe_solver != 1 && opt.ppe_solver != 3 && opt.ppe_solver != 4)
+    return fail(nullptr, IFX_ERR_INVALID, "ppe_solver: 1 (point Jacobi), 3 (red-black SOR) or 4 (multigrid); line SOR is not built");
+  if (opt.ppe_solver != 1 && opt.compat != IFX_COMPAT_FULL)
+    return fail(nullptr, IFX_ERR_INVALID, "red-black SOR / multigrid need IFX_COMPAT_FULL (the reference mode reproduces the reference's Jacobi)");
+  if (opt.ppe_solver != 1 && !(opt.ppe_omega > 0.0 && opt.ppe_omega < 2.0))
     return fail(nullptr, IFX_ERR_INVALID, "SOR needs 0 < ppe_omega < 2");
+  if (opt.ppe_solver == 4) {
+    int lx[IFX_MG_MAX_LEVELS], ly[IFX_MG_MAX_LEVELS];
+    if (mg_plan(in->nx - 2, in->ny - 2, lx, ly) < 2)
+      return fail(nullptr, IFX_ERR_INVALID, "multigrid needs even cell counts (>= 4) in both directions");
+    if (opt.nranks > 1) return fail(nullptr, IFX_ERR_INVALID, "multigrid is single-GPU for now (slab runs: ppe_solver 1 or 3)");
+  }
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
     cudaGetLastError();
@@ -422,6 +428,10 @@ extern "C" int ifx_destroy(ifx_solver* s) {
                     s->d_counters, s->d_rowcount, s->d_rowstart};
   for (int* f : ifields) if (f) cudaFree(f);
   for (double* t : s->tables) cudaFree(t);
+  for (int l = 1; l < s->mg_levels; l++) {
+    double* a[] = {s->mg[l].GE, s->mg[l].GN, s->mg[l].e, s->mg[l].R};
+    for (double* q : a) if (q) cudaFree(q);
+  }
   if (s->celltype) cudaFree(s->celltype);
   if (s->ctl) cudaFree(s->ctl);
   if (s->h_ctl) cudaFreeHost(s->h_ctl);
@@ -890,3 +900,160 @@ int ifx::run_ppe_loop(ifx_solver* s, ifx_step_stats* st, bool laplace_ref) {
   return IFX_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Poisson by geometric multigrid (PPE_Solver 4).  Semantics: oracle/ifx_oracle_mg.c + the solver-4
+// branch of orc_full_poisson (UNPINNED).  An "iteration" is one V(NU1, NU2) cycle; the stop rule is the reference's
+// (sum of the residual against ppe_tol, at most PPE_itermax iterations) and is evaluated, like everywhere else,
+// by the first fine-level half-sweep of the NEXT cycle, which is the only launch of a cycle that can end the loop —
+// the host looks at the control block once per cycle, right after it.
+// ------------------------------------------------------------------------------------------------
+static int mg_ensure(ifx_solver* s) {
+  if (s->mg_levels == 0) {
+    int lx[IFX_MG_MAX_LEVELS], ly[IFX_MG_MAX_LEVELS];
+    const int n = mg_plan(s->L.nx - 2, s->L.ny - 2, lx, ly);
+    if (n < 2) return fail(s, IFX_ERR_INVALID, "multigrid needs even cell counts (>= 4) in both directions");
+    for (int l = 1; l < n; l++) {
+      const size_t bytes = sizeof(double) * (size_t)(lx[l] + 2) * (ly[l] + 2);
+      s->mg[l].ncx = lx[l]; s->mg[l].ncy = ly[l];
+      double** a[] = {&s->mg[l].GE, &s->mg[l].GN, &s->mg[l].e, &s->mg[l].R};
+      for (double** q : a) {
+        IFX_CUDA(s, cudaMalloc(q, bytes));
+        IFX_CUDA(s, cudaMemsetAsync(*q, 0, bytes, s->stream));
+      }
+      s->mg_levels = l + 1;          // what ifx_destroy frees if a later allocation fails
+    }
+    s->mg_valid = false;
+  }
+  if (!s->mg_valid) {
+    for (int l = 1; l < s->mg_levels; l++) {
+      const size_t bytes = sizeof(double) * (size_t)(s->mg[l].ncx + 2) * (s->mg[l].ncy + 2);
+      IFX_CUDA(s, cudaMemsetAsync(s->mg[l].GE, 0, bytes, s->stream));
+      IFX_CUDA(s, cudaMemsetAsync(s->mg[l].GN, 0, bytes, s->stream));
+      s->launches++;
+      if (l == 1) IFX_CUDA(s, launch_mg_build1(s->L, s->M, s->celltype, s->mg[1], s->stream));
+      else IFX_CUDA(s, launch_mg_coarsen(s->mg[l - 1], s->mg[l], s->stream));
+    }
+    s->mg_valid = true;
+  }
+  return IFX_OK;
+}
+
+// coarse part of a V-cycle: mg[1].R is set; on return mg[1].e is the correction for level 0 (orc_mg_coarse_cycle)
+static int mg_coarse_cycle(ifx_solver* s) {
+  const int Lv = s->mg_levels;
+  const double omega = s->opt.ppe_omega;
+  auto smooth = [&](int l, int its) -> int {
+    for (int k = 0; k < its; k++)
+      for (int colour = 0; colour < 2; colour++) {
+        s->launches++;
+        IFX_CUDA(s, launch_mg_smooth(s->mg[l], colour, omega, s->stream));
+      }
+    return IFX_OK;
+  };
+  int rc;
+  for (int l = 1; l < Lv; l++) {
+    IFX_CUDA(s, cudaMemsetAsync(s->mg[l].e, 0, sizeof(double) * (size_t)(s->mg[l].ncx + 2) * (s->mg[l].ncy + 2), s->stream));
+    if ((rc = smooth(l, l == Lv - 1 ? ifx_mg_ncoarse(s->mg[l].ncx, s->mg[l].ncy) : IFX_MG_NU1)) != IFX_OK) return rc;
+    if (l < Lv - 1) {
+      s->launches++;
+      IFX_CUDA(s, launch_mg_restrict(s->mg[l], s->mg[l + 1], s->stream));
+    }
+  }
+  for (int l = Lv - 2; l >= 1; l--) {
+    s->launches++;
+    IFX_CUDA(s, launch_mg_prolong(s->mg[l + 1], s->mg[l], s->stream));
+    if ((rc = smooth(l, IFX_MG_NU2)) != IFX_OK) return rc;
+  }
+  return IFX_OK;
+}
+
+int ifx::run_ppe_multigrid(ifx_solver* s, ifx_step_stats* st) {
+  const Layout& L = s->L;
+  if (s->opt.nranks != 1) return fail(s, IFX_ERR_INVALID, "multigrid is single-GPU for now");
+  if (s->kernel_variant != 4) return fail(s, IFX_ERR_INVALID, "multigrid needs the default kernel variant");
+  const bool exact = s->opt.reduce_mode == IFX_REDUCE_REFERENCE;
+  const int itermax = s->in.PPE_itermax;
+  const int ry = rows_per_cta_for(s, 1);
+  const dim3 grid = tile_grid(s, ry, 1);
+  const size_t nblocks = (size_t)grid.x * grid.y;
+  int rc = ensure_partials(s, nblocks);
+  if (rc != IFX_OK) return rc;
+  if (exact && (rc = ensure_exact_buffers(s)) != IFX_OK) return rc;
+
+  IFX_CUDA(s, cudaEventRecord(s->ev[2], s->stream));
+  if ((rc = mg_ensure(s)) != IFX_OK) return rc;
+  const int base = s->cur_p;          // a red-black iteration leaves the iterate in the buffer it started in
+  IFX_CUDA(s, cudaMemsetAsync(s->ctl, 0, sizeof(LoopCtl), s->stream));
+  int K = 0, fallbacks = 0;
+  if (itermax > 0) {
+    PpeSweepArgs pa{};
+    pa.L = L; pa.M = s->M;
+    pa.rhs = s->rhs; pa.celltype = s->celltype;
+    pa.res = s->res_a; pa.partials = s->partials; pa.ctl = s->ctl;
+    pa.rows_per_cta = ry;
+    pa.rc.itermax = itermax; pa.rc.tol = s->opt.ppe_tol; pa.rc.use_second = 0;
+    pa.rc.test_abs = s->opt.ppe_abs_residual ? 1 : 0;
+    pa.rc.certify = exact ? 0 : 1;
+    pa.rc.band = rounding_band(s, nblocks, ry);
+    pa.sor = 1; pa.sor_omega = s->opt.ppe_omega;
+    const int fo[1] = {4 + base};
+    make_halo_ctx(s, 1, 1, fo, &pa.hx);           // single GPU: an empty context
+    // colour-0 half-sweep base -> partner; eval > 0: it also evaluates the residual of iterate `eval` (the input)
+    auto red = [&](int eval, int decide, int force, bool write_res) -> int {
+      pa.pC = s->p[base]; pa.pT = s->p[base ^ 1];
+      pa.rc.eval_iter = eval; pa.rc.decide = decide;
+      pa.sor_colour = 0; pa.force = force;
+      return launch_ppe_sweep(s, pa, grid, false, write_res);
+    };
+    auto black = [&]() -> int {                   // colour-1 half-sweep partner -> base, no residual bookkeeping
+      pa.pC = s->p[base ^ 1]; pa.pT = s->p[base];
+      pa.rc.eval_iter = 0; pa.rc.decide = 0;
+      pa.sor_colour = 1; pa.force = 0;
+      return launch_ppe_sweep(s, pa, grid, false, false);
+    };
+    for (int c = 1;; c++) {
+      // first smoothing iteration of cycle c; its colour-0 half evaluates the residual of iterate c-1 and decides
+      if ((rc = red(c - 1, exact ? 0 : 1, 0, exact)) != IFX_OK) return rc;
+      if (exact && c > 1 && (rc = exact_decide(s, pa.rc, false)) != IFX_OK) return rc;
+      if ((rc = black()) != IFX_OK) return rc;
+      if ((rc = fetch_ctl(s)) != IFX_OK) return rc;
+      if (s->h_ctl->done && s->h_ctl->ambiguous) {
+        // the fused sum is within rounding of the tolerance: re-evaluate in the reference's summation order
+        fallbacks++;
+        if ((rc = ensure_exact_buffers(s)) != IFX_OK) return rc;
+        pa.res = s->res_a;
+        if ((rc = red(c - 1, 0, 1, true)) != IFX_OK) return rc;
+        if ((rc = exact_decide(s, pa.rc, false)) != IFX_OK) return rc;
+        if ((rc = fetch_ctl(s)) != IFX_OK) return rc;
+        if (!s->h_ctl->done && (rc = black()) != IFX_OK) return rc;     // not converged after all: second half
+      }
+      if (s->h_ctl->done) break;
+      if (c >= itermax + 1) return fail(s, IFX_ERR_STATE, "multigrid loop ran past PPE_itermax without a decision");
+      for (int k = 1; k < IFX_MG_NU1; k++) {
+        if ((rc = red(0, 0, 0, false)) != IFX_OK) return rc;
+        if ((rc = black()) != IFX_OK) return rc;
+      }
+      s->launches++;
+      IFX_CUDA(s, launch_mg_restrict_fine(L, s->M, s->celltype, s->rhs, s->p[base], s->mg[1], s->stream));
+      if ((rc = mg_coarse_cycle(s)) != IFX_OK) return rc;
+      s->launches++;
+      IFX_CUDA(s, launch_mg_prolong_fine(L, s->celltype, s->mg[1], s->p[base], s->stream));
+      for (int k = 0; k < IFX_MG_NU2; k++) {
+        if ((rc = red(0, 0, 0, false)) != IFX_OK) return rc;
+        if ((rc = black()) != IFX_OK) return rc;
+      }
+    }
+    K = s->h_ctl->iter;
+  }
+  s->cur_p = base;
+  IFX_CUDA(s, cudaEventRecord(s->ev[3], s->stream));
+  IFX_CUDA(s, cudaEventSynchronize(s->ev[3]));
+  if (st) {
+    st->ppe_sweeps = K;
+    st->ppe_residual = (itermax > 0) ? (s->opt.ppe_abs_residual ? s->h_ctl->res1 : s->h_ctl->res0) : 1.0;
+    st->exact_fallbacks += fallbacks;
+    cudaEventElapsedTime(&st->ms_ppe, s->ev[2], s->ev[3]);
+  }
+  return IFX_OK;
+}

@@ -207,6 +207,7 @@ extern "C" int ifx_iblank_update(ifx_solver* s, ifx_step_stats* st) {
                                              "use fewer ranks for this grid");
   }
   s->bodies_dirty = false;
+  s->mg_valid = false;             // so did the open faces the coarse-level conductances are made of
   s->faces_valid = false;          // closed faces moved with the bodies
   s->state_bc_fresh = false;
   IFX_CUDA(s, cudaEventRecord(s->ev[7], s->stream));
@@ -291,7 +292,7 @@ extern "C" int ifx_ppe_solve(ifx_solver* s, ifx_step_stats* st) {
   // a15: source term from the predicted velocities (their ring and ghost cells were refreshed by the predictor)
   s->launches++;
   IFX_CUDA(s, launch_ppe_rhs(s->L, s->M, s->celltype, s->d_ub, s->d_vb, s->u[s->cur_uv], s->v[s->cur_uv], s->rhs, s->stream));
-  if ((rc = run_ppe_loop(s, st, false)) != IFX_OK) return rc;
+  if ((rc = (s->opt.ppe_solver == 4 ? run_ppe_multigrid(s, st) : run_ppe_loop(s, st, false))) != IFX_OK) return rc;
   if ((rc = full_refresh_pressure_bc(s, s->cur_p)) != IFX_OK) return rc;
   IFX_CUDA(s, cudaStreamSynchronize(s->stream));
   return IFX_OK;

@@ -12,7 +12,12 @@
 // out as fma() and mirrors the contraction nvcc emits for the reference kernels (read from the
 // reference's sm_100 PTX/SASS), so results are bit-identical to the reference CUDA build.
 #pragma once
+// IFX_HOST_SHIM: tests/cuda_host_shim.h compiles the thread-per-cell kernels (kernels_mg.cu, kernels_diag.cu) with
+// g++ and runs their grids serially on the CPU, so their arithmetic and indexing are checked against the oracle
+// in the CPU test suite as well as on the GPU.  Test infrastructure only; the product is never built this way.
+#ifndef IFX_HOST_SHIM
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 
 #define IFX_PADL 15
@@ -116,6 +121,7 @@ struct HaloCtx {
   unsigned* mail_seq[IFX_MAX_RANKS];
 };
 
+#ifndef IFX_HOST_SHIM
 __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
   unsigned v;
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -134,5 +140,6 @@ __device__ __forceinline__ double warp_sum(double v) {
   for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
   return v;
 }
+#endif  // IFX_HOST_SHIM
 
 }  // namespace ifx

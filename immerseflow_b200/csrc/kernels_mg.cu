@@ -1,0 +1,185 @@
+// kernels_mg.cu — transfer and coarse-level kernels of the geometric multigrid V-cycle (PPE_Solver 4).
+// Semantics and operation order: oracle/ifx_oracle_mg.c (PARITY UNPINNED); compiled -fmad=false, every fused
+// multiply-add is explicit, so each level is bit-identical to the oracle.
+//
+// One thread per (coarse) cell, no shared memory, no inter-thread communication: the whole file also compiles as
+// plain C++ under tests/cuda_host_shim.h, where the CPU test suite runs every kernel against the oracle.
+// HBM traffic per V-cycle beyond the fine-level smoothing (25 B/cell per half-sweep, kernels_v4.cu):
+// residual + restriction 17 B per fine cell read + 2 B written, prolongation 17 B read + 8 B written; all coarse
+// levels together hold 1/3 of the fine cells.
+#include "multigrid.cuh"
+#include "stencil_math.cuh"
+
+#ifdef IFX_HOST_SHIM
+#define IFX_KLAUNCH(k, grid, block, st, ...) (shim_launch((grid), (block), [&] { k(__VA_ARGS__); }), cudaSuccess)
+#else
+#define IFX_KLAUNCH(k, grid, block, st, ...) (k<<<(grid), (block), 0, (st)>>>(__VA_ARGS__), cudaGetLastError())
+#endif
+
+namespace ifx {
+
+constexpr int MG_BX = 32, MG_BY = 8;
+
+static inline dim3 mg_grid(int ncx, int ncy) { return dim3((ncx + MG_BX - 1) / MG_BX, (ncy + MG_BY - 1) / MG_BY, 1); }
+
+// index into a level's ghost-inclusive array
+__device__ __forceinline__ size_t cidx(int I, int J, int NX) { return (size_t)I + (size_t)J * NX; }
+
+// see dir_scale in the oracle: the factor 1/2 of a coarse face only in a direction the point smoother smooths
+__device__ __forceinline__ void mg_dir_scale(double sx, double sy, double& ax, double& ay) {
+  ax = (sx >= 0.25 * sy) ? 0.5 : 1.0;
+  ay = (sy >= 0.25 * sx) ? 0.5 : 1.0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// level-1 conductances from the grid metrics and the cell types (oracle: build_level1)
+// ---------------------------------------------------------------------------------------------
+static __global__ void k_mg_build1(Layout L, Metrics M, const uint8_t* __restrict__ ct, MgLevel c) {
+  const int I = 1 + blockIdx.x * blockDim.x + threadIdx.x, J = 1 + blockIdx.y * blockDim.y + threadIdx.y;
+  if (I > c.ncx || J > c.ncy) return;
+  const int i = 2 * I, j = 2 * J;               // children: columns i-1, i; rows j-1, j
+  double ge[2] = {0.0, 0.0}, gn[2] = {0.0, 0.0};
+#pragma unroll
+  for (int k = 0; k < 2; k++) {
+    const int jj = j - 1 + k, ii = i - 1 + k;
+    const size_t oe = lidx(L, i, jj - L.j0), on = lidx(L, ii, j - L.j0);
+    if (i <= L.nx - 3 && ct[oe] == IFX_FLUID && ct[oe + 1] == IFX_FLUID) ge[k] = (2.0 * M.dy[jj]) / (M.dx[i] + M.dx[i + 1]);
+    if (j <= L.ny - 3 && ct[on] == IFX_FLUID && ct[on + L.pitch] == IFX_FLUID) gn[k] = (2.0 * M.dx[ii]) / (M.dy[j] + M.dy[j + 1]);
+  }
+  const double sx = ge[0] + ge[1], sy = gn[0] + gn[1];
+  double ax, ay;
+  mg_dir_scale(sx, sy, ax, ay);
+  const size_t o = cidx(I, J, c.ncx + 2);
+  c.GE[o] = ax * sx;
+  c.GN[o] = ay * sy;
+}
+
+// level l+1 conductances from level l (oracle: build_coarser)
+static __global__ void k_mg_coarsen(MgLevel f, MgLevel c) {
+  const int I = 1 + blockIdx.x * blockDim.x + threadIdx.x, J = 1 + blockIdx.y * blockDim.y + threadIdx.y;
+  if (I > c.ncx || J > c.ncy) return;
+  const int i = 2 * I, j = 2 * J, nxl = f.ncx + 2;
+  const double sx = f.GE[cidx(i, j - 1, nxl)] + f.GE[cidx(i, j, nxl)];
+  const double sy = f.GN[cidx(i - 1, j, nxl)] + f.GN[cidx(i, j, nxl)];
+  double ax, ay;
+  mg_dir_scale(sx, sy, ax, ay);
+  const size_t o = cidx(I, J, c.ncx + 2);
+  c.GE[o] = ax * sx;
+  c.GN[o] = ay * sy;
+}
+
+// ---------------------------------------------------------------------------------------------
+// R1 = sum over the four children of (rhs - A p) dx_i dy_j, fluid children only (oracle: orc_mg_restrict_fine);
+// (A p) with the closed-face substitutions of the general Poisson sweep
+// ---------------------------------------------------------------------------------------------
+static __global__ void k_mg_restrict_fine(Layout L, Metrics M, const uint8_t* __restrict__ ct, const double* __restrict__ rhs,
+                                          const double* __restrict__ p, MgLevel c) {
+  const int I = 1 + blockIdx.x * blockDim.x + threadIdx.x, J = 1 + blockIdx.y * blockDim.y + threadIdx.y;
+  if (I > c.ncx || J > c.ncy) return;
+  double r[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const int i = 2 * I - 1 + (k & 1), j = 2 * J - 1 + (k >> 1);
+    const size_t o = lidx(L, i, j - L.j0);
+    r[k] = 0.0;
+    if (ct[o] != IFX_FLUID) continue;
+    const double pc = p[o];
+    const double pw = (i == 1 || ct[o - 1] != IFX_FLUID) ? pc : p[o - 1];
+    const double pe = (i == L.nx - 2 || ct[o + 1] != IFX_FLUID) ? pc : p[o + 1];
+    const double ps = (j == 1 || ct[o - L.pitch] != IFX_FLUID) ? pc : p[o - L.pitch];
+    const double pn = (j == L.ny - 2 || ct[o + L.pitch] != IFX_FLUID) ? pc : p[o + L.pitch];
+    const double cP = -(M.pp_sx[i] + M.pp_sy[j]);                                       // PPESolver.cu:93-94
+    const double q = ppe_apply(pc, cP, pw, M.pp_cW[i], pe, M.pp_cE[i], pn, M.pp_cN[j], ps, M.pp_cS[j]);
+    r[k] = (rhs[o] - q) * (M.dx[i] * M.dy[j]);
+  }
+  c.R[cidx(I, J, c.ncx + 2)] = (r[0] + r[1]) + (r[2] + r[3]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// one colour of red-black SOR on a coarse level, in place: cells of one colour are not neighbours
+// (oracle: orc_mg_smooth)
+// ---------------------------------------------------------------------------------------------
+static __global__ void k_mg_smooth(MgLevel l, int colour, double omega) {
+  const int I = 1 + blockIdx.x * blockDim.x + threadIdx.x, J = 1 + blockIdx.y * blockDim.y + threadIdx.y;
+  if (I > l.ncx || J > l.ncy || ((I + J + colour) & 1)) return;
+  const int NX = l.ncx + 2;
+  const size_t o = cidx(I, J, NX);
+  const double ge = l.GE[o], gw = l.GE[o - 1], gn = l.GN[o], gs = l.GN[o - NX];
+  const double D = (ge + gw) + (gn + gs);
+  if (!(D > 0.0)) return;
+  double t = ge * l.e[o + 1];
+  t = fma(gw, l.e[o - 1], t);
+  t = fma(gn, l.e[o + NX], t);
+  t = fma(gs, l.e[o - NX], t);
+  const double ej = (t - l.R[o]) / D;
+  const double ec = l.e[o];
+  l.e[o] = ec + omega * (ej - ec);
+}
+
+// R_{l+1} = sum over the four children of (R - (sum G e_nb - D e)) (oracle: orc_mg_restrict)
+static __global__ void k_mg_restrict(MgLevel f, MgLevel c) {
+  const int I = 1 + blockIdx.x * blockDim.x + threadIdx.x, J = 1 + blockIdx.y * blockDim.y + threadIdx.y;
+  if (I > c.ncx || J > c.ncy) return;
+  const int nxl = f.ncx + 2;
+  double r[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const size_t o = cidx(2 * I - 1 + (k & 1), 2 * J - 1 + (k >> 1), nxl);
+    const double ge = f.GE[o], gw = f.GE[o - 1], gn = f.GN[o], gs = f.GN[o - nxl];
+    const double D = (ge + gw) + (gn + gs);
+    r[k] = 0.0;
+    if (!(D > 0.0)) continue;
+    double t = ge * f.e[o + 1];
+    t = fma(gw, f.e[o - 1], t);
+    t = fma(gn, f.e[o + nxl], t);
+    t = fma(gs, f.e[o - nxl], t);
+    r[k] = f.R[o] - fma(-D, f.e[o], t);
+  }
+  c.R[cidx(I, J, c.ncx + 2)] = (r[0] + r[1]) + (r[2] + r[3]);
+}
+
+// e_l += e_{l+1}(parent) on the active cells of level l (oracle: orc_mg_prolong)
+static __global__ void k_mg_prolong(MgLevel c, MgLevel f) {
+  const int i = 1 + blockIdx.x * blockDim.x + threadIdx.x, j = 1 + blockIdx.y * blockDim.y + threadIdx.y;
+  if (i > f.ncx || j > f.ncy) return;
+  const int nxl = f.ncx + 2;
+  const size_t o = cidx(i, j, nxl);
+  const double D = (f.GE[o] + f.GE[o - 1]) + (f.GN[o] + f.GN[o - nxl]);
+  if (!(D > 0.0)) return;
+  f.e[o] = f.e[o] + c.e[cidx((i + 1) / 2, (j + 1) / 2, c.ncx + 2)];
+}
+
+// p += e_1(parent) on fluid cells (oracle: orc_mg_prolong_fine)
+static __global__ void k_mg_prolong_fine(Layout L, const uint8_t* __restrict__ ct, MgLevel c, double* __restrict__ p) {
+  const int i = 1 + blockIdx.x * blockDim.x + threadIdx.x, j = 1 + blockIdx.y * blockDim.y + threadIdx.y;
+  if (i > L.nx - 2 || j > L.ny - 2) return;
+  const size_t o = lidx(L, i, j - L.j0);
+  if (ct[o] != IFX_FLUID) return;
+  p[o] = p[o] + c.e[cidx((i + 1) / 2, (j + 1) / 2, c.ncx + 2)];
+}
+
+// ---------------------------------------------------------------------------------------------
+cudaError_t launch_mg_build1(const Layout& L, const Metrics& M, const uint8_t* celltype, MgLevel c, cudaStream_t st) {
+  return IFX_KLAUNCH(k_mg_build1, mg_grid(c.ncx, c.ncy), dim3(MG_BX, MG_BY, 1), st, L, M, celltype, c);
+}
+cudaError_t launch_mg_coarsen(MgLevel f, MgLevel c, cudaStream_t st) {
+  return IFX_KLAUNCH(k_mg_coarsen, mg_grid(c.ncx, c.ncy), dim3(MG_BX, MG_BY, 1), st, f, c);
+}
+cudaError_t launch_mg_restrict_fine(const Layout& L, const Metrics& M, const uint8_t* celltype, const double* rhs,
+                                    const double* p, MgLevel c, cudaStream_t st) {
+  return IFX_KLAUNCH(k_mg_restrict_fine, mg_grid(c.ncx, c.ncy), dim3(MG_BX, MG_BY, 1), st, L, M, celltype, rhs, p, c);
+}
+cudaError_t launch_mg_smooth(MgLevel l, int colour, double omega, cudaStream_t st) {
+  return IFX_KLAUNCH(k_mg_smooth, mg_grid(l.ncx, l.ncy), dim3(MG_BX, MG_BY, 1), st, l, colour, omega);
+}
+cudaError_t launch_mg_restrict(MgLevel f, MgLevel c, cudaStream_t st) {
+  return IFX_KLAUNCH(k_mg_restrict, mg_grid(c.ncx, c.ncy), dim3(MG_BX, MG_BY, 1), st, f, c);
+}
+cudaError_t launch_mg_prolong(MgLevel c, MgLevel f, cudaStream_t st) {
+  return IFX_KLAUNCH(k_mg_prolong, mg_grid(f.ncx, f.ncy), dim3(MG_BX, MG_BY, 1), st, c, f);
+}
+cudaError_t launch_mg_prolong_fine(const Layout& L, const uint8_t* celltype, MgLevel c, double* p, cudaStream_t st) {
+  return IFX_KLAUNCH(k_mg_prolong_fine, mg_grid(L.nx - 2, L.ny - 2), dim3(MG_BX, MG_BY, 1), st, L, celltype, c, p);
+}
+
+}  // namespace ifx

@@ -37,7 +37,7 @@ struct Args {
   bool reference_log = false;
   bool exact = false;
   bool checkpoints = false;      // write restart files every Write_Interval steps and after the last one
-  int ppe_solver = 0;            // 0: PPE_Solver of inputs.txt; 1 point Jacobi; 3 red-black SOR (full mode)
+  int ppe_solver = 0;            // 0: PPE_Solver of inputs.txt; 1 point Jacobi; 3 red-black SOR; 4 multigrid (full mode)
   double ppe_omega = 0.0;        // 0: w-PPE of inputs.txt (an integer there)
   std::string restart;           // explicit restart file (default when Restart != 0: <results>/restart.<Restart_Time>.ifx)
   int device = 0;
@@ -48,13 +48,14 @@ static void usage() {
       "immerseflow [--input FILE] [--xgrid FILE] [--ygrid FILE] [--stretched] [--results DIR]\n"
       "            [--mode reference|full] [--bodies FILE] [--steps N] [--write-every-step]\n"
       "            [--reference-log] [--exact-reduction] [--checkpoints] [--restart FILE] [--device K]\n"
-      "            [--ppe-solver 1|3] [--ppe-omega W]\n"
+      "            [--ppe-solver 1|3|4] [--ppe-omega W]\n"
       "  defaults reproduce the reference binary run from src/: ../inputs/inputs.txt, ../inputs/{x,y}grid.dat2,\n"
       "  tmax predictor steps, ../results/{final_results,uc,vc}.dat.  --stretched picks ../inputs/{x,y}grid.dat.\n"
       "  inputs.txt `Write Interval` N: results are (re)written every N steps as well as after the last one; with\n"
       "  --checkpoints a restart file <results>/restart.<step, 7 digits>.ifx goes with them.  `Restart 1 T` in inputs.txt\n"
       "  (or --restart FILE) continues from <results>/restart.<T>.ifx: steps T+1 .. tmax, bit-identical to an unbroken run.\n"
       "  --ppe-solver 3 (or PPE_Solver 3 in inputs.txt; full mode): red-black SOR with factor --ppe-omega / w-PPE.\n"
+      "  --ppe-solver 4: geometric multigrid V(2,2) cycles (even cell counts; PPE_itermax then counts cycles).\n"
       "  --bodies FILE (full mode): `nbodies`, then per body `nmarkers ub vb` and nmarkers lines `x y` (counter-clockwise).\n";
 }
 

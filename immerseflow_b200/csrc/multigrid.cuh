@@ -1,0 +1,46 @@
+// multigrid.cuh — geometric multigrid for the pressure-Poisson equation (PPE_Solver 4).
+// Semantics: oracle/ifx_oracle_mg.c (PARITY UNPINNED — the reference always runs point Jacobi, PPESolver.cu:13-31).
+//
+// Level 0 is the solver's grid (padded layout, smoothed by the red-black SOR instantiation of the bulk-copy sweep
+// kernel, kernels_v4.cu).  Level l >= 1 merges 2x2 cells of level l-1 and lives in four dense ghost-inclusive arrays
+// of (ncx+2) x (ncy+2) doubles: GE / GN = conductance of a cell's east / north face, e = correction, R = right-hand
+// side of the volume-form error equation  sum_f G_f (e_nb - e_C) = R_C.
+#pragma once
+#include "common.cuh"
+
+#define IFX_MG_MAX_LEVELS 16
+#define IFX_MG_NU1 2          // pre-smoothing red-black SOR iterations per level
+#define IFX_MG_NU2 2          // post-smoothing
+// iterations on the coarsest level: max(32, its cell count), at most 2048 (a grid like 200 x 120 stops at 25 x 15)
+inline int ifx_mg_ncoarse(int ncx, int ncy) { const int n = ncx * ncy; return n < 32 ? 32 : (n > 2048 ? 2048 : n); }
+
+namespace ifx {
+
+struct MgLevel {
+  int ncx, ncy;               // cells (without the ghost ring)
+  double* GE; double* GN; double* e; double* R;
+};
+
+// levels for an ncx x ncy grid: halve while both counts are even and >= 4.  Returns the number of levels incl. level 0.
+inline int mg_plan(int ncx, int ncy, int* lx, int* ly) {
+  int n = 1;
+  lx[0] = ncx; ly[0] = ncy;
+  while (n < IFX_MG_MAX_LEVELS && lx[n - 1] % 2 == 0 && ly[n - 1] % 2 == 0 && lx[n - 1] >= 4 && ly[n - 1] >= 4) {
+    lx[n] = lx[n - 1] / 2; ly[n] = ly[n - 1] / 2;
+    n++;
+  }
+  return n;
+}
+
+// kernels_mg.cu.  The GE / GN arrays of the target level must be zero-filled before the two build launches
+// (their ghost ring is never written).
+cudaError_t launch_mg_build1(const Layout& L, const Metrics& M, const uint8_t* celltype, MgLevel c, cudaStream_t st);
+cudaError_t launch_mg_coarsen(MgLevel f, MgLevel c, cudaStream_t st);
+cudaError_t launch_mg_restrict_fine(const Layout& L, const Metrics& M, const uint8_t* celltype, const double* rhs,
+                                    const double* p, MgLevel c, cudaStream_t st);
+cudaError_t launch_mg_smooth(MgLevel l, int colour, double omega, cudaStream_t st);
+cudaError_t launch_mg_restrict(MgLevel f, MgLevel c, cudaStream_t st);
+cudaError_t launch_mg_prolong(MgLevel c, MgLevel f, cudaStream_t st);
+cudaError_t launch_mg_prolong_fine(const Layout& L, const uint8_t* celltype, MgLevel c, double* p, cudaStream_t st);
+
+}  // namespace ifx

@@ -4,6 +4,7 @@
 #pragma once
 #include "../../include/immerseflow_c.h"
 #include "kernels.cuh"
+#include "multigrid.cuh"
 
 #include <string>
 #include <vector>
@@ -80,6 +81,11 @@ struct ifx_solver {
   unsigned seq[IFX_SYNC_GROUPS] = {0, 0, 0};   // launches per sync group (identical on every rank)
   unsigned mseq = 0;                           // residual-mailbox tag
 
+  // geometric multigrid (PPE_Solver 4): coarse levels 1 .. mg_levels-1, allocated on first use
+  int mg_levels = 0;
+  ifx::MgLevel mg[IFX_MG_MAX_LEVELS] = {};
+  bool mg_valid = false;             // the conductances match the current cell types (cleared by ifx_iblank_update)
+
   int kernel_variant = 4;            // 1: register-rolled direct loads (kernels_ad.cu / kernels_ppe.cu, reference mode only)
                                      // 4: bulk-copy row pipeline, lean interior path (kernels_v4.cu, default)
                                      // (IFX_KERNEL_VARIANT; variants 2, 3 were stepping stones, see profiles/)
@@ -105,6 +111,7 @@ double rounding_band(const ifx_solver* s, size_t nblocks, int rows_per_cta);
 void fill_bc(const ifx_solver* s, double* two_u, double* two_v);
 int run_ad_loop(ifx_solver* s, ifx_step_stats* st, bool full);
 int run_ppe_loop(ifx_solver* s, ifx_step_stats* st, bool laplace_ref);
+int run_ppe_multigrid(ifx_solver* s, ifx_step_stats* st);
 int full_refresh_velocity_bc(ifx_solver* s, int buf);
 int full_refresh_pressure_bc(ifx_solver* s, int buf);
 // slabs

@@ -3,7 +3,9 @@
 // explicitly.  Compiled with -fmad=false: nothing here is contracted further.  Shared by every kernel
 // variant so that all of them are bit-identical to each other and to the reference build.
 #pragma once
+#ifndef IFX_HOST_SHIM
 #include <cuda_runtime.h>
+#endif
 
 namespace ifx {
 

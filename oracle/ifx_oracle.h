@@ -146,7 +146,37 @@ int orc_full_poisson(orc_full* s, double* stats);
 void orc_ppe_sor_halfsweep(int nx, int ny, const double* cP, const double* cxm, const double* cxp, const double* cym,
                            const double* cyp, const unsigned char* celltype, const double* rhs, int colour, double omega,
                            const double* p, double* p_new);
-void orc_full_set_ppe_solver(orc_full* s, int solver /* 1 Jacobi, 3 red-black SOR */, double omega);
+void orc_full_set_ppe_solver(orc_full* s, int solver /* 1 Jacobi, 3 red-black SOR, 4 multigrid */, double omega);
+/* V-cycle shape of PPE_Solver 4 (defaults ORC_MG_NU1/NU2/NCOARSE) */
+void orc_full_set_mg(orc_full* s, int nu1, int nu2, int ncoarse);
+
+/* ---- geometric multigrid (ifx_oracle_mg.c; UNPINNED) ------------------------------ */
+#define ORC_MG_MAX_LEVELS 16
+#define ORC_MG_NU1 2
+#define ORC_MG_NU2 2
+#define ORC_MG_NCOARSE 0    /* 0: max(32, cells of the coarsest level), at most 2048 (orc_mg_ncoarse) */
+typedef struct orc_mg orc_mg;
+int orc_mg_plan(int ncx, int ncy, int* lx, int* ly);
+int orc_mg_ncoarse(int ncx, int ncy);
+orc_mg* orc_mg_create(int nx, int ny, const double* dx, const double* dy, const unsigned char* celltype);
+void orc_mg_destroy(orc_mg* m);
+int orc_mg_levels(const orc_mg* m);
+int orc_mg_get(const orc_mg* m, int l, int which, double* out, int* ncx, int* ncy);
+void orc_mg_restrict_fine(int nx, int ny, const double* dx, const double* dy, const double* cP, const double* cxm,
+                          const double* cxp, const double* cym, const double* cyp, const unsigned char* ct,
+                          const double* rhs, const double* p, int NX, int NY, double* R1);
+void orc_mg_smooth(int NX, int NY, const double* GE, const double* GN, const double* R, int colour, double omega,
+                   double* e);
+void orc_mg_restrict(int nxl, const double* GE, const double* GN, const double* R, const double* e, int NX, int NY,
+                     double* Rc);
+void orc_mg_prolong(int nxl, int nyl, const double* GE, const double* GN, int NX, const double* ec, double* e);
+void orc_mg_prolong_fine(int nx, int ny, const unsigned char* ct, int NX, const double* e1, double* p);
+void orc_mg_coarse_cycle(orc_mg* m, int nu1, int nu2, int ncoarse, double omega);
+void orc_mg_vcycle(orc_mg* m, int nx, int ny, const double* dx, const double* dy, const double* cP, const double* cxm,
+                   const double* cxp, const double* cym, const double* cyp, const unsigned char* ct, const double* rhs,
+                   int nu1, int nu2, int ncoarse, double omega, double* p, double* pT);
+/* the multigrid hierarchy of the last orc_full_poisson call with solver 4 (NULL before) */
+const orc_mg* orc_full_mg(const orc_full* s);
 void orc_full_correct(orc_full* s);
 void orc_full_step(orc_full* s, double* stats);
 int orc_full_get(orc_full* s, int field, double* out);

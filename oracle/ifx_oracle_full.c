@@ -437,8 +437,10 @@ struct orc_full {
   int nbodies; int* off; double *xm, *ym, *ub, *vb;
   int ngc, *cell, *stencil, *body; double *wd, *wn, *bi, *ip;
   int faces_valid;
-  int ppe_solver;                     /* 1: point Jacobi (the reference's sweep), 3: red-black SOR */
+  int ppe_solver;                     /* 1: point Jacobi (the reference's sweep), 3: red-black SOR, 4: multigrid */
   double w_ppe;
+  int mg_nu1, mg_nu2, mg_ncoarse;
+  orc_mg* mg;                         /* hierarchy of the last multigrid solve (rebuilt per solve: bodies may move) */
 };
 
 orc_full* orc_full_create(int nx, int ny, const double* xf, const double* yf, double dt, double Re, int AD_itermax,
@@ -448,6 +450,7 @@ orc_full* orc_full_create(int nx, int ny, const double* xf, const double* yf, do
   s->nx = nx; s->ny = ny; s->dt = dt; s->Re = Re; s->AD_itermax = AD_itermax; s->PPE_itermax = PPE_itermax;
   s->ad_tol = ad_tol; s->ppe_tol = ppe_tol; s->ppe_abs = ppe_abs;
   s->ppe_solver = 1; s->w_ppe = 1.0;
+  s->mg_nu1 = ORC_MG_NU1; s->mg_nu2 = ORC_MG_NU2; s->mg_ncoarse = ORC_MG_NCOARSE;
   for (int q = 0; q < 4; q++) { s->two_bc_u[q] = bc_u[q] * 2.0; s->two_bc_v[q] = bc_v[q] * 2.0; }   /* W, E, S, N */
   s->xc = (double*)calloc(nx, 8); s->yc = (double*)calloc(ny, 8);
   s->dx = (double*)calloc(N, 8); s->dy = (double*)calloc(N, 8);
@@ -469,6 +472,7 @@ static void free_gc(orc_full* s) {
 void orc_full_destroy(orc_full* s) {
   if (!s) return;
   free_gc(s);
+  orc_mg_destroy(s->mg);
   free(s->xc); free(s->yc); free(s->dx); free(s->dy); free(s->u); free(s->v); free(s->p); free(s->uf); free(s->vf);
   free(s->rhs); free(s->sx); free(s->sy); free(s->celltype); free(s->iblank); free(s->body_of);
   free(s->off); free(s->xm); free(s->ym); free(s->ub); free(s->vb);
@@ -588,8 +592,15 @@ int orc_full_poisson(orc_full* s, double* stats) {
   memcpy(pT, pc, N * 8);
   double R = 1.0, Rabs = 1.0;
   int iter = 0;
+  if (s->ppe_solver == 4) {          /* an "iteration" is one V-cycle */
+    orc_mg_destroy(s->mg);
+    s->mg = orc_mg_create(nx, ny, s->dx, s->dy, s->celltype);
+  }
   while ((s->ppe_abs ? Rabs : R) > s->ppe_tol && iter < s->PPE_itermax) {
-    if (s->ppe_solver == 3) {       /* red-black SOR: two half-sweeps, the iterate ends up where it started */
+    if (s->ppe_solver == 4) {
+      orc_mg_vcycle(s->mg, nx, ny, s->dx, s->dy, cP, cxm, cxp, cym, cyp, s->celltype, s->rhs, s->mg_nu1, s->mg_nu2,
+                    s->mg_ncoarse, s->w_ppe, pc, pT);
+    } else if (s->ppe_solver == 3) {       /* red-black SOR: two half-sweeps, the iterate ends up where it started */
       orc_ppe_sor_halfsweep(nx, ny, cP, cxm, cxp, cym, cyp, s->celltype, s->rhs, 0, s->w_ppe, pc, pT);
       orc_ppe_sor_halfsweep(nx, ny, cP, cxm, cxp, cym, cyp, s->celltype, s->rhs, 1, s->w_ppe, pT, pc);
     } else {
@@ -613,6 +624,8 @@ int orc_full_poisson(orc_full* s, double* stats) {
 }
 
 void orc_full_set_ppe_solver(orc_full* s, int solver, double omega) { s->ppe_solver = solver; s->w_ppe = omega; }
+void orc_full_set_mg(orc_full* s, int nu1, int nu2, int ncoarse) { s->mg_nu1 = nu1; s->mg_nu2 = nu2; s->mg_ncoarse = ncoarse; }
+const orc_mg* orc_full_mg(const orc_full* s) { return s->mg; }
 
 void orc_full_correct(orc_full* s) {
   const size_t N = (size_t)s->nx * s->ny;

@@ -29,7 +29,7 @@ _lib = None
 def lib():
     global _lib
     if _lib is None:
-        srcs = [os.path.join(ORACLE_DIR, f) for f in ("ifx_oracle.c", "ifx_oracle_full.c", "ifx_oracle.h")]
+        srcs = [os.path.join(ORACLE_DIR, f) for f in ("ifx_oracle.c", "ifx_oracle_full.c", "ifx_oracle_mg.c", "ifx_oracle.h")]
         if not os.path.exists(LIB) or any(os.path.getmtime(s) > os.path.getmtime(LIB) for s in srcs):
             subprocess.check_call(["make", "-C", ORACLE_DIR, "libifx_oracle.so"], stdout=subprocess.DEVNULL)
         _lib = C.CDLL(LIB)
@@ -174,6 +174,9 @@ class FullSolver:
     def set_ppe_solver(self, solver, omega):
         lib().orc_full_set_ppe_solver.argtypes = [C.c_void_p, C.c_int, C.c_double]
         lib().orc_full_set_ppe_solver(self.h, int(solver), float(omega))
+
+    def set_mg(self, nu1, nu2, ncoarse):
+        lib().orc_full_set_mg(self.h, int(nu1), int(nu2), int(ncoarse))
 
     def predictor(self):
         lib().orc_full_predictor(self.h, P(self.stats)); return self.stats.copy()

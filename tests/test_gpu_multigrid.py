@@ -1,0 +1,64 @@
+"""PPE_Solver 4 — geometric multigrid on the GPU through the C-ABI, against oracle/ifx_oracle_mg.c:
+pressure bit-exact after every step, identical V-cycle counts.  PARITY UNPINNED (the reference has no multigrid);
+tests/test_mg_shim.py runs the same kernel source on the CPU."""
+import numpy as np
+import pytest
+
+import immerseflow_b200 as ifx
+import _oracle as orc
+from test_gpu_full_parity import pair, assert_same_fields
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("reduce_mode", [ifx.IFX_REDUCE_FUSED, ifx.IFX_REDUCE_REFERENCE])
+@pytest.mark.parametrize("ncx,ncy,body", [(64, 64, False), (96, 64, True), (200, 120, True)])
+def test_multigrid_matches_oracle(ncx, ncy, body, reduce_mode):
+    xf, yf = ifx.uniform_faces(ncx, ncx / 64.0), ifx.uniform_faces(ncy, ncy / 64.0)
+    u0, v0, _ = orc.initial_condition(orc.Grid(xf, yf))
+    g, o = pair(xf, yf, 1e-3, 150.0, 25, 40, ppe_tol=1e-5, reduce_mode=reduce_mode, ppe_solver=4, ppe_omega=1.0)
+    o.set_ppe_solver(4, 1.0)
+    with g:
+        if body:
+            bodies = [orc.circle_markers(0.3, 0.6, 0.11, 40), orc.ellipse_markers(0.9, 0.4, 0.2, 0.07, 0.4, 48)]
+            g.set_bodies(bodies); o.set_bodies(bodies)
+        g.initializeData()
+        g.set("u", u0); g.set("v", v0); g.set("p", np.zeros_like(u0))
+        o.set("u", u0); o.set("v", v0)
+        o.update_ib()
+        for step in range(3):
+            st = g.step(); so = o.step()
+            assert (st.ad_iters, st.ppe_sweeps) == (int(so[0]), int(so[3])), f"step {step}"
+            assert_same_fields(g, o, tag=f"step {step}")
+            assert st.ppe_sweeps < 40 and st.ppe_residual <= 1e-5, (st.ppe_sweeps, st.ppe_residual)
+            if reduce_mode == ifx.IFX_REDUCE_REFERENCE:
+                assert st.ppe_residual == so[4]
+    o.close()
+
+
+def test_multigrid_moving_body_rebuilds_the_hierarchy():
+    xf, yf = ifx.uniform_faces(128, 2.0), ifx.uniform_faces(64, 1.0)
+    g, o = pair(xf, yf, 2e-3, 100.0, 25, 30, ppe_tol=1e-5, ppe_solver=4, ppe_omega=1.0)
+    o.set_ppe_solver(4, 1.0)
+    with g:
+        g.initializeData()
+        n = g.field_size("u")
+        g.set("u", np.ones(n)); g.set("v", np.zeros(n)); g.set("p", np.zeros(n))
+        o.set("u", np.ones(n)); o.set("v", np.zeros(n))
+        for step in range(3):
+            bodies = [orc.circle_markers(0.6 + 0.05 * step, 0.5, 0.15, 48)]
+            g.set_bodies(bodies, [(0.5, 0.0)]); o.set_bodies(bodies, [(0.5, 0.0)])
+            o.update_ib()
+            st = g.step(); so = o.step()
+            assert (st.ad_iters, st.ppe_sweeps) == (int(so[0]), int(so[3])), f"step {step}"
+            assert_same_fields(g, o, tag=f"step {step}")
+    o.close()
+
+
+def test_multigrid_needs_even_cell_counts_and_full_mode():
+    inp = ifx.make_input(51, 64, 1e-3, 150.0)
+    with pytest.raises(ifx.IfxError, match="even cell counts"):
+        ifx.ImmerseFlow(inp, ifx.uniform_faces(51, 1.0), ifx.uniform_faces(64, 1.0), compat=ifx.IFX_COMPAT_FULL, ppe_solver=4)
+    inp = ifx.make_input(64, 64, 1e-3, 150.0)
+    with pytest.raises(ifx.IfxError, match="IFX_COMPAT_FULL"):
+        ifx.ImmerseFlow(inp, ifx.uniform_faces(64, 1.0), ifx.uniform_faces(64, 1.0), ppe_solver=4)
