@@ -37,6 +37,7 @@ C_ABI_SYMBOLS = [
     "ifx_checkpoint_write", "ifx_checkpoint_read",
     "ifx_ad_solve", "ifx_ppe_solve", "ifx_correct", "ifx_step", "ifx_reduce_sum", "ifx_get_residual_history",
     "ifx_set_bodies", "ifx_iblank_update", "ifx_ghost_cell_count", "ifx_get_ghost_cells",
+    "ifx_probe", "ifx_body_forces",
     "ifx_ipc_export", "ifx_ipc_connect",
     "ifx_set_stream", "ifx_synchronize", "ifx_launch_count",
 ]
@@ -120,6 +121,8 @@ def load_library() -> C.CDLL:
     lib.ifx_set_bodies.argtypes = [vp, C.c_int, ip, dp, dp, dp, dp]
     lib.ifx_ghost_cell_count.argtypes = [vp]
     lib.ifx_get_ghost_cells.argtypes = [vp, ip, ip, dp, dp, dp, C.c_int]
+    lib.ifx_probe.argtypes = [vp, C.c_int, dp, dp, dp, dp, dp]
+    lib.ifx_body_forces.argtypes = [vp, dp, C.c_int]
     lib.ifx_ipc_export.argtypes = [vp, C.c_char_p]
     lib.ifx_ipc_connect.argtypes = [vp, C.c_char_p, C.c_int]
     lib.ifx_set_stream.argtypes = [vp, vp]
@@ -353,6 +356,21 @@ class ImmerseFlow:
                                                      sten.ctypes.data_as(C.POINTER(C.c_int)), _dp(w), _dp(bi), _dp(ip), n),
                         "ifx_get_ghost_cells")
         return {"cell": cell, "stencil": sten, "weights": w, "bi": bi, "ip": ip}
+
+    # ---- diagnostics ----------------------------------------------------------------
+    def probe(self, x, y):
+        """u, v, p interpolated at the points (x[k], y[k])."""
+        x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1)
+        y = np.ascontiguousarray(y, dtype=np.float64).reshape(-1)
+        u, v, p = np.zeros(x.size), np.zeros(x.size), np.zeros(x.size)
+        self._check(self.lib.ifx_probe(self._h, x.size, _dp(x), _dp(y), _dp(u), _dp(v), _dp(p)), "ifx_probe")
+        return u, v, p
+
+    def body_forces(self, nbodies: int) -> np.ndarray:
+        """(nbodies, 4): pressure force x, y and viscous force x, y on every body."""
+        F = np.zeros((max(nbodies, 1), 4))
+        self._check(self.lib.ifx_body_forces(self._h, _dp(F.reshape(-1)), max(nbodies, 1)), "ifx_body_forces")
+        return F[:nbodies]
 
     # ---- state ------------------------------------------------------------------------------------
     def field_size(self, name: str) -> int:

@@ -36,6 +36,8 @@ SOURCES = [
     ("kernels_full.cu", True),
     ("kernels_ib.cu", True),
     ("kernels_mg.cu", True),
+    ("kernels_diag.cu", True),
+    ("capi_diag.cu", True),
     ("kernels_ic.cu", False),   # default flags on purpose: same libdevice expansion as the reference build
     ("io.cpp", True),
 ]

@@ -201,6 +201,16 @@ int ifx_ghost_cell_count(const ifx_solver* s);
 int ifx_get_ghost_cells(ifx_solver* s, int* cell_id, int* stencil_id, double* weights,
                         double* bi_xy, double* ip_xy, int capacity);
 
+/* ---- diagnostics (IFX_COMPAT_FULL, single GPU; SURVEY 8(f)-4 — the reference has none, its predecessor did:
+ *      test/UTIL_PRE_SIM.f90:172-201) ------------------------------------------------------------------------- */
+/* u, v, p interpolated bilinearly at n points (x[k], y[k]); ghost cells take part with their boundary values,
+ * cells inside a body are dropped from the interpolation */
+int ifx_probe(ifx_solver* s, int n, const double* x, const double* y, double* u, double* v, double* p);
+/* surface force on every body, 4 doubles per body: pressure force x, y, viscous force x, y (per unit span; the drag
+ * coefficient is 2 (Fpx + Fvx) / (U^2 D)).  Two probes per marker segment, 1.5 and 3 cell diagonals off the surface:
+ * wall pressure by linear extrapolation, wall shear from a second-order one-sided difference. */
+int ifx_body_forces(ifx_solver* s, double* forces, int capacity_bodies);
+
 /* ---- multi-GPU slabs (one process per GPU; halos move over NVLink peer mappings) -------------- */
 #define IFX_IPC_HANDLE_BYTES 128
 /* export this rank's exchange segment; the launcher all-gathers the handles (torch.distributed) */

@@ -150,6 +150,23 @@ void orc_full_set_ppe_solver(orc_full* s, int solver /* 1 Jacobi, 3 red-black SO
 /* V-cycle shape of PPE_Solver 4 (defaults ORC_MG_NU1/NU2/NCOARSE) */
 void orc_full_set_mg(orc_full* s, int nu1, int nu2, int ncoarse);
 
+/* ---- diagnostics (ifx_oracle_diag.c; UNPINNED) -------------------------------------- */
+void orc_interp_setup(int nx, int ny, const double* xc, const double* yc, const unsigned char* ct, double x, double y,
+                      int* sten, double* w);
+void orc_probe(int nx, int ny, const double* xc, const double* yc, const unsigned char* ct, const double* u,
+               const double* v, const double* p, int npts, const double* px, const double* py, double* ou, double* ov,
+               double* op);
+void orc_force_geometry(int nx, int ny, const double* xc, const double* yc, int nseg_total, const int* off, int nbodies,
+                        const double* xm, const double* ym, double* geo);
+void orc_force_sum(int nbodies, const int* off, const double* geo, const double* pu, const double* pv, const double* pp,
+                   const double* ub, const double* vb, double Re, double* F);
+void orc_body_forces(int nx, int ny, const double* xc, const double* yc, const unsigned char* ct, double Re, int nbodies,
+                     const int* off, const double* xm, const double* ym, const double* ub, const double* vb,
+                     const double* u, const double* v, const double* p, double* F);
+/* the full solver's own state: F = 4 per body; probe of its u, v, p */
+void orc_full_body_forces(orc_full* s, double* F);
+void orc_full_probe(orc_full* s, int npts, const double* px, const double* py, double* ou, double* ov, double* op);
+
 /* ---- geometric multigrid (ifx_oracle_mg.c; UNPINNED) ------------------------------ */
 #define ORC_MG_MAX_LEVELS 16
 #define ORC_MG_NU1 2

@@ -643,6 +643,14 @@ void orc_full_step(orc_full* s, double* stats) {
   orc_full_correct(s);
 }
 
+void orc_full_body_forces(orc_full* s, double* F) {
+  orc_body_forces(s->nx, s->ny, s->xc, s->yc, s->celltype, s->Re, s->nbodies, s->off, s->xm, s->ym, s->ub, s->vb, s->u,
+                  s->v, s->p, F);
+}
+void orc_full_probe(orc_full* s, int npts, const double* px, const double* py, double* ou, double* ov, double* op) {
+  orc_probe(s->nx, s->ny, s->xc, s->yc, s->celltype, s->u, s->v, s->p, npts, px, py, ou, ov, op);
+}
+
 /* field ids follow include/immerseflow_c.h's ifx_field */
 static double* full_field(orc_full* s, int f) {
   switch (f) {

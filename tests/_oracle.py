@@ -29,7 +29,7 @@ _lib = None
 def lib():
     global _lib
     if _lib is None:
-        srcs = [os.path.join(ORACLE_DIR, f) for f in ("ifx_oracle.c", "ifx_oracle_full.c", "ifx_oracle_mg.c", "ifx_oracle.h")]
+        srcs = [os.path.join(ORACLE_DIR, f) for f in ("ifx_oracle.c", "ifx_oracle_full.c", "ifx_oracle_mg.c", "ifx_oracle_diag.c", "ifx_oracle.h")]
         if not os.path.exists(LIB) or any(os.path.getmtime(s) > os.path.getmtime(LIB) for s in srcs):
             subprocess.check_call(["make", "-C", ORACLE_DIR, "libifx_oracle.so"], stdout=subprocess.DEVNULL)
         _lib = C.CDLL(LIB)
@@ -177,6 +177,17 @@ class FullSolver:
 
     def set_mg(self, nu1, nu2, ncoarse):
         lib().orc_full_set_mg(self.h, int(nu1), int(nu2), int(ncoarse))
+
+    def body_forces(self, nbodies):
+        F = np.zeros((nbodies, 4))
+        lib().orc_full_body_forces(self.h, P(F.reshape(-1)))
+        return F
+
+    def probe(self, x, y):
+        x = np.ascontiguousarray(x, dtype=np.float64); y = np.ascontiguousarray(y, dtype=np.float64)
+        u, v, p = np.zeros(x.size), np.zeros(x.size), np.zeros(x.size)
+        lib().orc_full_probe(self.h, x.size, P(x), P(y), P(u), P(v), P(p))
+        return u, v, p
 
     def predictor(self):
         lib().orc_full_predictor(self.h, P(self.stats)); return self.stats.copy()
