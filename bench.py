@@ -43,6 +43,9 @@ def parse_args():
     ap.add_argument("--cpu-sample-rows", type=int, default=192, help="rows of the workload the CPU baseline runs on")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-handles", type=int, default=3,
+                    help="simulations in flight in the end-to-end measurement: 3 = one uploading its next state, one stepping, "
+                         "one downloading its result (PCIe both ways overlapped with the kernels); 1 = upload, step, download in series")
     ap.add_argument("--mode", default="full", choices=["full", "reference"],
                     help="full: complete fractional step (predictor + Poisson with source + projection); reference: what the "
                          "reference binary's time step runs (predictor) + its Laplace-Jacobi Poisson kernels")
@@ -308,21 +311,26 @@ def main():
     if args.emulate_slab_of and world == 1:
         jb, je = slabs.partition_rows(inp.ny, args.emulate_slab_of)[0]
     full = args.mode == "full"
-    s = ifx.ImmerseFlow(inp, xf, yf, device=dev, sweeps_per_batch=args.ppe_sweeps + 1, rank=rank, nranks=world,
-                        j_begin=jb, j_end=je, compat=ifx.IFX_COMPAT_FULL if full else ifx.IFX_COMPAT_REFERENCE,
-                        ppe_abs_residual=1 if full else 0)
-    s.initializeData()
-    # The reference starts the Poisson solve from p == 0 (preSim.cu:67), which makes most quotients exact zeros for
-    # the first sweeps — an arithmetic special case.  The bench uses a smooth non-zero pressure field so that every
-    # fp64 division takes the normal-operand path a converging solve sees.
-    n_p = s.field_size("p")
-    lo = jb - 1
-    jj, ii = np.divmod(np.arange(n_p, dtype=np.float64), float(inp.nx))
-    jj += lo
-    s.set("p", 50.0 + 40.0 * np.sin(ii * (6.283185307179586 / inp.nx)) * np.cos(jj * (6.283185307179586 / inp.ny)))
-    del jj, ii
-    if world > 1:
-        slabs.connect(s, dist)
+
+    def make_solver():
+        """one simulation: handle, initial state, slab connections"""
+        h = ifx.ImmerseFlow(inp, xf, yf, device=dev, sweeps_per_batch=args.ppe_sweeps + 1, rank=rank, nranks=world,
+                            j_begin=jb, j_end=je, compat=ifx.IFX_COMPAT_FULL if full else ifx.IFX_COMPAT_REFERENCE,
+                            ppe_abs_residual=1 if full else 0)
+        h.initializeData()
+        # The reference starts the Poisson solve from p == 0 (preSim.cu:67), which makes most quotients exact zeros for
+        # the first sweeps — an arithmetic special case.  The bench uses a smooth non-zero pressure field so that every
+        # fp64 division takes the normal-operand path a converging solve sees.
+        n_p = h.field_size("p")
+        jj, ii = np.divmod(np.arange(n_p, dtype=np.float64), float(inp.nx))
+        jj += jb - 1
+        h.set("p", 50.0 + 40.0 * np.sin(ii * (6.283185307179586 / inp.nx)) * np.cos(jj * (6.283185307179586 / inp.ny)))
+        del jj, ii
+        if world > 1:
+            slabs.connect(h, dist)
+        return h
+
+    s = make_solver()
 
     def barrier():
         if world > 1:
@@ -331,16 +339,17 @@ def main():
 
     step_no = [0]
 
-    def one_step():
+    def one_step(h=None):
+        h = h or s
         if full:
             if nb:
                 b, vel = bodies_at(nb, step_no[0], args.dt)
-                s.set_bodies(b, vel)
+                h.set_bodies(b, vel)
                 step_no[0] += 1
-            st = s.step()
+            st = h.step()
             return st, st
-        a = s.ADsolver()
-        b = s.PPESolver()
+        a = h.ADsolver()
+        b = h.PPESolver()
         return a, b
 
     for _ in range(args.warmup):
@@ -392,26 +401,68 @@ def main():
                 "projection_ms": float(np.mean(cor_ms)), "iblank_ghost_cells_ms": float(np.mean(ib_ms)),
                 "ghost_cells": int(s.lib.ifx_ghost_cell_count(s._h))}
 
-    # ---- e2e: same step through the C-ABI with HOST buffers (pinned): H2D of u,v,p, step, D2H of u,v,p
+    # ---- e2e: the same step through the C-ABI with HOST buffers (pinned): every step uploads its u, v, p and downloads
+    # the u, v, p it produced.  One handle does that in series (H2D, kernels, D2H: the PCIe time of 2 x 3 fields is
+    # longer than the step).  The default keeps `--e2e-handles` simulations in flight, each on its own stream: while
+    # one steps, the next one's state is uploading and the previous one's result is downloading, so both PCIe
+    # directions overlap the kernels; pipeline fill and drain are inside the timed region.
     e2e = None
     if not args.no_e2e:
         n = s.field_size("u")
-        host = {k: torch.empty(n, dtype=torch.float64, pin_memory=True).numpy() for k in ("u", "v", "p")}
-        for k in host:
-            s.get(k, host[k])
-        reps = max(1, min(args.steps, 2))
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(reps):
-            for k in host:
-                s.set(k, host[k])
-            one_step()
-            for k in host:
-                s.get(k, host[k])
-        barrier()
+        names = ("u", "v", "p")
+        host_in = {k: torch.empty(n, dtype=torch.float64, pin_memory=True).numpy() for k in names}
+        for k in names:
+            s.get(k, host_in[k])
+        nh = max(1, min(args.e2e_handles, 3))
+        reps = max(1, args.steps)
+        if nh == 1:
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                for k in names:
+                    s.set(k, host_in[k])
+                one_step()
+                for k in names:
+                    s.get(k, host_in[k])
+            barrier()
+        else:
+            sims = [s] + [make_solver() for _ in range(nh - 1)]
+            host_out = [{k: torch.empty(n, dtype=torch.float64, pin_memory=True).numpy() for k in names} for _ in range(2)]
+            for h in sims[1:]:                     # every handle allocates its lazily sized buffers before the clock starts
+                one_step(h)
+            barrier()
+            for h in sims:
+                h.synchronize()
+            t0 = time.perf_counter()
+            for k in names:                        # fill: the first simulation's state
+                sims[0].set_async(k, host_in[k])
+            for it in range(reps):
+                cur, nxt, prv = sims[it % nh], sims[(it + 1) % nh], sims[(it - 1) % nh]
+                cur.synchronize()                  # its upload has landed (and its older download left host_out[it % 2] free)
+                if it >= 1:                        # (download before upload: with 2 handles they share a stream)
+                    for k in names:
+                        prv.get_async(k, host_out[it % 2][k])
+                if it + 1 < reps:
+                    for k in names:
+                        nxt.set_async(k, host_in[k])
+                one_step(cur)
+            for k in names:                        # drain: the last result
+                sims[(reps - 1) % nh].get_async(k, host_out[reps % 2][k])
+            for h in sims:
+                h.synchronize()
+            barrier()
         te = (time.perf_counter() - t0) / reps
+        if world > 1:
+            t = torch.tensor([te], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            te = float(t.item())
         e2e = {"value": cells / te / 1e6, "unit": METRIC, "h2d_bytes_per_step": 3 * 8 * n, "d2h_bytes_per_step": 3 * 8 * n,
-               "ms_per_step": te * 1e3}
+               "ms_per_step": te * 1e3, "steps": reps,
+               "pipeline": (f"{nh} simulations in flight (upload | step | download overlapped), fill + drain timed" if nh > 1
+                            else "upload, step, download in series")}
+        if nh > 1:
+            for h in sims[1:]:
+                h.close()
 
     line = {"metric": METRIC, "value": value, "unit": METRIC, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": wall_ms, "device_ms_per_step": dev_ms, "higher_is_better": True, "scaling": "strong",

@@ -37,7 +37,7 @@ C_ABI_SYMBOLS = [
     "ifx_checkpoint_write", "ifx_checkpoint_read",
     "ifx_ad_solve", "ifx_ppe_solve", "ifx_correct", "ifx_step", "ifx_reduce_sum", "ifx_get_residual_history",
     "ifx_set_bodies", "ifx_iblank_update", "ifx_ghost_cell_count", "ifx_get_ghost_cells",
-    "ifx_probe", "ifx_body_forces",
+    "ifx_probe", "ifx_body_forces", "ifx_set_field_async", "ifx_get_field_async",
     "ifx_ipc_export", "ifx_ipc_connect",
     "ifx_set_stream", "ifx_synchronize", "ifx_launch_count",
 ]
@@ -111,6 +111,8 @@ def load_library() -> C.CDLL:
     lib.ifx_field_size.restype = C.c_size_t
     lib.ifx_set_field.argtypes = [vp, C.c_int, dp, C.c_size_t]
     lib.ifx_get_field.argtypes = [vp, C.c_int, dp, C.c_size_t]
+    lib.ifx_set_field_async.argtypes = [vp, C.c_int, dp, C.c_size_t]
+    lib.ifx_get_field_async.argtypes = [vp, C.c_int, dp, C.c_size_t]
     lib.ifx_save_field.argtypes = [vp, C.c_int, C.c_char_p]
     lib.ifx_checkpoint_write.argtypes = [vp, C.c_char_p, C.c_longlong, C.c_double]
     lib.ifx_checkpoint_read.argtypes = [vp, C.c_char_p, C.POINTER(C.c_longlong), C.POINTER(C.c_double)]
@@ -386,6 +388,18 @@ class ImmerseFlow:
     def set(self, name: str, values: np.ndarray) -> None:
         v = np.ascontiguousarray(values, dtype=np.float64).reshape(-1)
         self._check(self.lib.ifx_set_field(self._h, FIELD[name], _dp(v), v.size), f"ifx_set_field({name})")
+
+    def set_async(self, name: str, values: np.ndarray) -> None:
+        """Enqueue the upload on this handle's stream; `values` must be a contiguous float64 array in page-locked memory
+        that stays untouched until synchronize() or the next blocking call on this handle."""
+        if values.dtype != np.float64 or not values.flags["C_CONTIGUOUS"]:
+            raise IfxError("set_async needs a contiguous float64 array (no hidden copy may be made)")
+        self._check(self.lib.ifx_set_field_async(self._h, FIELD[name], _dp(values), values.size), f"ifx_set_field_async({name})")
+
+    def get_async(self, name: str, out: np.ndarray) -> None:
+        if out.dtype != np.float64 or not out.flags["C_CONTIGUOUS"]:
+            raise IfxError("get_async needs a contiguous float64 array")
+        self._check(self.lib.ifx_get_field_async(self._h, FIELD[name], _dp(out), out.size), f"ifx_get_field_async({name})")
 
     def set_stream(self, cuda_stream: int) -> None:
         self._check(self.lib.ifx_set_stream(self._h, C.c_void_p(cuda_stream)), "ifx_set_stream")

@@ -523,7 +523,7 @@ extern "C" size_t ifx_field_size(const ifx_solver* s, ifx_field f) {
   return (size_t)v.width * v.rows;
 }
 
-extern "C" int ifx_set_field(ifx_solver* s, ifx_field f, const double* host, size_t n) {
+static int set_field_impl(ifx_solver* s, ifx_field f, const double* host, size_t n, bool sync) {
   if (!s || !host) return IFX_ERR_INVALID;
   IFX_CUDA(s, cudaSetDevice(s->device));
   FieldView v;
@@ -543,11 +543,16 @@ extern "C" int ifx_set_field(ifx_solver* s, ifx_field f, const double* host, siz
     if (f != IFX_FIELD_P) { s->faces_valid = false; s->state_bc_fresh = false; }
   }
   if (f == IFX_FIELD_UF || f == IFX_FIELD_VF) s->faces_valid = true;
-  IFX_CUDA(s, cudaStreamSynchronize(s->stream));
+  if (sync) IFX_CUDA(s, cudaStreamSynchronize(s->stream));
   return IFX_OK;
 }
 
-extern "C" int ifx_get_field(ifx_solver* s, ifx_field f, double* host, size_t n) {
+extern "C" int ifx_set_field(ifx_solver* s, ifx_field f, const double* host, size_t n) { return set_field_impl(s, f, host, n, true); }
+// enqueue only: the copy runs on the handle's stream, ahead of whatever is called next on this handle; `host` (pinned
+// memory, or the copy is not asynchronous) must stay untouched until ifx_synchronize or the next blocking call
+extern "C" int ifx_set_field_async(ifx_solver* s, ifx_field f, const double* host, size_t n) { return set_field_impl(s, f, host, n, false); }
+
+static int get_field_impl(ifx_solver* s, ifx_field f, double* host, size_t n, bool sync) {
   if (!s || !host) return IFX_ERR_INVALID;
   IFX_CUDA(s, cudaSetDevice(s->device));
   FieldView v;
@@ -556,6 +561,7 @@ extern "C" int ifx_get_field(ifx_solver* s, ifx_field f, double* host, size_t n)
   if (n != (size_t)v.width * v.rows) return fail(s, IFX_ERR_INVALID, "size mismatch");
   const Layout& L = s->L;
   if (v.table) { std::memcpy(host, v.table, sizeof(double) * n); return IFX_OK; }
+  if (v.is_u8 && !sync) return fail(s, IFX_ERR_INVALID, "cell types are read synchronously");
   if (v.is_u8) {
     double* tmp = nullptr;
     IFX_CUDA(s, cudaMalloc(&tmp, sizeof(double) * n));
@@ -569,9 +575,13 @@ extern "C" int ifx_get_field(ifx_solver* s, ifx_field f, double* host, size_t n)
   }
   IFX_CUDA(s, cudaMemcpy2DAsync(host, sizeof(double) * v.width, v.dev + lidx(L, v.i0, v.jl0), sizeof(double) * L.pitch,
                                 sizeof(double) * v.width, v.rows, cudaMemcpyDeviceToHost, s->stream));
-  IFX_CUDA(s, cudaStreamSynchronize(s->stream));
+  if (sync) IFX_CUDA(s, cudaStreamSynchronize(s->stream));
   return IFX_OK;
 }
+
+extern "C" int ifx_get_field(ifx_solver* s, ifx_field f, double* host, size_t n) { return get_field_impl(s, f, host, n, true); }
+// enqueue only: `host` (pinned) holds the field once ifx_synchronize (or any blocking call on this handle) returned
+extern "C" int ifx_get_field_async(ifx_solver* s, ifx_field f, double* host, size_t n) { return get_field_impl(s, f, host, n, false); }
 
 // saveDataToFile (postSim.cu:10-39): D2H then the Tecplot writer.
 extern "C" int ifx_save_field(ifx_solver* s, ifx_field f, const char* filename) {

@@ -160,6 +160,12 @@ int ifx_initialize(ifx_solver* s);
 size_t ifx_field_size(const ifx_solver* s, ifx_field f);      /* number of doubles */
 int ifx_set_field(ifx_solver* s, ifx_field f, const double* host, size_t n);
 int ifx_get_field(ifx_solver* s, ifx_field f, double* host, size_t n);
+/* The same, enqueued on the handle's stream without waiting: the transfer overlaps whatever OTHER handles are running
+ * (several handles of one process = several simulations in flight: one uploading its next state, one stepping, one
+ * downloading its result — bench.py's end-to-end pipeline).  `host` must be page-locked and stay untouched until
+ * ifx_synchronize() or the next blocking call on this handle returns. */
+int ifx_set_field_async(ifx_solver* s, ifx_field f, const double* host, size_t n);
+int ifx_get_field_async(ifx_solver* s, ifx_field f, double* host, size_t n);
 /* replaces saveDataToFile(), postSim.cu:10-39: D2H + Tecplot ASCII */
 int ifx_save_field(ifx_solver* s, ifx_field f, const char* filename);
 /* Restart files: what `Restart` / `Restart_Time` / `Write_Interval` of inputs.txt ask for (parsed at
