@@ -312,11 +312,11 @@ def main():
         jb, je = slabs.partition_rows(inp.ny, args.emulate_slab_of)[0]
     full = args.mode == "full"
 
-    def make_solver():
+    def make_solver(zero_copy_control=0):
         """one simulation: handle, initial state, slab connections"""
         h = ifx.ImmerseFlow(inp, xf, yf, device=dev, sweeps_per_batch=args.ppe_sweeps + 1, rank=rank, nranks=world,
                             j_begin=jb, j_end=je, compat=ifx.IFX_COMPAT_FULL if full else ifx.IFX_COMPAT_REFERENCE,
-                            ppe_abs_residual=1 if full else 0)
+                            ppe_abs_residual=1 if full else 0, zero_copy_control=zero_copy_control)
         h.initializeData()
         # The reference starts the Poisson solve from p == 0 (preSim.cu:67), which makes most quotients exact zeros for
         # the first sweeps — an arithmetic special case.  The bench uses a smooth non-zero pressure field so that every
@@ -426,9 +426,10 @@ def main():
                     s.get(k, host_in[k])
             barrier()
         else:
-            sims = [s] + [make_solver() for _ in range(nh - 1)]
+            # handles whose control traffic does not queue behind the bulk transfers (ifx_options.zero_copy_control)
+            sims = [make_solver(1) for _ in range(nh)]
             host_out = [{k: torch.empty(n, dtype=torch.float64, pin_memory=True).numpy() for k in names} for _ in range(2)]
-            for h in sims[1:]:                     # every handle allocates its lazily sized buffers before the clock starts
+            for h in sims:                         # every handle allocates its lazily sized buffers before the clock starts
                 one_step(h)
             barrier()
             for h in sims:
@@ -461,7 +462,9 @@ def main():
                "pipeline": (f"{nh} simulations in flight (upload | step | download overlapped), fill + drain timed" if nh > 1
                             else "upload, step, download in series")}
         if nh > 1:
-            for h in sims[1:]:
+            if world > 1:
+                dist.barrier()                     # nobody frees a segment a neighbour may still be storing into
+            for h in sims:
                 h.close()
 
     line = {"metric": METRIC, "value": value, "unit": METRIC, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

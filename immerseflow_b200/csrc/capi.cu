@@ -170,10 +170,22 @@ static int reduce_reference_order(ifx_solver* s, const double* d_in, size_t n, d
   return IFX_OK;
 }
 
-int ifx::fetch_ctl(ifx_solver* s) {
-  IFX_CUDA(s, cudaMemcpyAsync(s->h_ctl, s->ctl, sizeof(LoopCtl), cudaMemcpyDeviceToHost, s->stream));
+// a few bytes device -> page-locked host, then wait for the stream.  zero_copy_control: a kernel stores them straight
+// into the host buffer (no copy engine, so a bulk download of another handle cannot hold them up)
+int ifx::fetch_small(ifx_solver* s, void* host_pinned, const void* dev, size_t bytes) {
+  if (s->opt.zero_copy_control) {
+    s->launches++;
+    IFX_CUDA(s, launch_copy_words(host_pinned, dev, bytes, s->stream));
+  } else {
+    IFX_CUDA(s, cudaMemcpyAsync(host_pinned, dev, bytes, cudaMemcpyDeviceToHost, s->stream));
+  }
   IFX_CUDA(s, cudaStreamSynchronize(s->stream));
   return IFX_OK;
+}
+
+int ifx::fetch_ctl(ifx_solver* s) {
+  static_assert(sizeof(LoopCtl) % 4 == 0, "LoopCtl is copied in 4-byte words");
+  return fetch_small(s, s->h_ctl, s->ctl, sizeof(LoopCtl));
 }
 
 void ifx::fill_bc(const ifx_solver* s, double* two_u, double* two_v) {
@@ -402,6 +414,7 @@ extern "C" int ifx_create(const ifx_input* in, const double* xf, const double* y
   launch_fill_u8(s->celltype, s->field_elems, IFX_FLUID, s->stream);
   s->launches++;
   if (cudaMalloc(&s->ctl, sizeof(LoopCtl)) != cudaSuccess || cudaMallocHost(&s->h_ctl, sizeof(LoopCtl)) != cudaSuccess ||
+      cudaMallocHost(&s->h_counters, sizeof(int) * 4) != cudaSuccess ||
       cudaMalloc(&s->red_out, sizeof(double) * 4) != cudaSuccess) {
     s->err = "control block allocation failed";
     return bail(IFX_ERR_CUDA);
@@ -435,6 +448,8 @@ extern "C" int ifx_destroy(ifx_solver* s) {
   if (s->celltype) cudaFree(s->celltype);
   if (s->ctl) cudaFree(s->ctl);
   if (s->h_ctl) cudaFreeHost(s->h_ctl);
+  if (s->h_counters) cudaFreeHost(s->h_counters);
+  if (s->h_stage) cudaFreeHost(s->h_stage);
   for (auto& ev : s->ev) if (ev) cudaEventDestroy(ev);
   if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
   delete s;
@@ -523,6 +538,11 @@ extern "C" size_t ifx_field_size(const ifx_solver* s, ifx_field f) {
   return (size_t)v.width * v.rows;
 }
 
+static int transfer_block_rows(int width) {
+  const long long rows = (16LL << 20) / ((long long)width * (long long)sizeof(double));
+  return (int)std::max(1LL, rows);
+}
+
 static int set_field_impl(ifx_solver* s, ifx_field f, const double* host, size_t n, bool sync) {
   if (!s || !host) return IFX_ERR_INVALID;
   IFX_CUDA(s, cudaSetDevice(s->device));
@@ -532,9 +552,16 @@ static int set_field_impl(ifx_solver* s, ifx_field f, const double* host, size_t
   if (v.table || v.is_u8) return fail(s, IFX_ERR_INVALID, "field is read-only");
   if (n != (size_t)v.width * v.rows) return fail(s, IFX_ERR_INVALID, "size mismatch");
   const Layout& L = s->L;
-  IFX_CUDA(s, cudaMemcpy2DAsync(v.dev + lidx(L, v.i0, v.jl0), sizeof(double) * L.pitch, host,
-                                sizeof(double) * v.width, sizeof(double) * v.width, v.rows,
-                                cudaMemcpyHostToDevice, s->stream));
+  // async transfers go in row blocks of ~16 MB: a copy engine serves its queue in order, and the few-byte control
+  // copies of a step running on ANOTHER handle (stop flags, ghost-cell counts, marker uploads) must be able to slip in
+  // between the blocks instead of waiting behind a whole field (measured: one whole-field copy per direction stalls
+  // the concurrent step by the full transfer time)
+  const int blk = sync ? v.rows : transfer_block_rows(v.width);
+  for (int r0 = 0; r0 < v.rows; r0 += blk) {
+    const int nr = std::min(blk, v.rows - r0);
+    IFX_CUDA(s, cudaMemcpy2DAsync(v.dev + lidx(L, v.i0, v.jl0 + r0), sizeof(double) * L.pitch, host + (size_t)r0 * v.width,
+                                  sizeof(double) * v.width, sizeof(double) * v.width, nr, cudaMemcpyHostToDevice, s->stream));
+  }
   if (f == IFX_FIELD_U || f == IFX_FIELD_V || f == IFX_FIELD_P) {
     // keep the ping-pong partner's ghost ring consistent (a freshly set state has no history)
     double* other = (f == IFX_FIELD_U) ? s->u[s->cur_uv ^ 1] : (f == IFX_FIELD_V) ? s->v[s->cur_uv ^ 1] : s->p[s->cur_p ^ 1];
@@ -573,8 +600,12 @@ static int get_field_impl(ifx_solver* s, ifx_field f, double* host, size_t n, bo
     IFX_CUDA(s, e);
     return IFX_OK;
   }
-  IFX_CUDA(s, cudaMemcpy2DAsync(host, sizeof(double) * v.width, v.dev + lidx(L, v.i0, v.jl0), sizeof(double) * L.pitch,
-                                sizeof(double) * v.width, v.rows, cudaMemcpyDeviceToHost, s->stream));
+  const int blk = sync ? v.rows : transfer_block_rows(v.width);
+  for (int r0 = 0; r0 < v.rows; r0 += blk) {
+    const int nr = std::min(blk, v.rows - r0);
+    IFX_CUDA(s, cudaMemcpy2DAsync(host + (size_t)r0 * v.width, sizeof(double) * v.width, v.dev + lidx(L, v.i0, v.jl0 + r0),
+                                  sizeof(double) * L.pitch, sizeof(double) * v.width, nr, cudaMemcpyDeviceToHost, s->stream));
+  }
   if (sync) IFX_CUDA(s, cudaStreamSynchronize(s->stream));
   return IFX_OK;
 }

@@ -115,15 +115,37 @@ extern "C" int ifx_set_bodies(ifx_solver* s, int nbodies, const int* offsets, co
   }
   if (!s->d_body_off) IFX_CUDA(s, cudaMalloc(&s->d_body_off, sizeof(int) * 65));
   if (!s->d_bbox) IFX_CUDA(s, cudaMalloc(&s->d_bbox, sizeof(double) * 4 * 64));
-  IFX_CUDA(s, cudaMemcpyAsync(s->d_body_off, s->h_body_off.data(), sizeof(int) * s->h_body_off.size(), cudaMemcpyHostToDevice, s->stream));
-  if (nm) {
-    IFX_CUDA(s, cudaMemcpyAsync(s->d_xm, s->h_xm.data(), sizeof(double) * nm, cudaMemcpyHostToDevice, s->stream));
-    IFX_CUDA(s, cudaMemcpyAsync(s->d_ym, s->h_ym.data(), sizeof(double) * nm, cudaMemcpyHostToDevice, s->stream));
+  // uploads: body offsets, markers, bounding boxes, body velocities
+  struct Up { void* dst; const void* src; size_t bytes; };
+  const Up ups[] = {{s->d_body_off, s->h_body_off.data(), sizeof(int) * s->h_body_off.size()},
+                    {s->d_xm, s->h_xm.data(), sizeof(double) * nm},
+                    {s->d_ym, s->h_ym.data(), sizeof(double) * nm},
+                    {s->d_bbox, s->h_bbox.data(), sizeof(double) * s->h_bbox.size()},
+                    {s->d_ub, s->h_ub.data(), sizeof(double) * 64},
+                    {s->d_vb, s->h_vb.data(), sizeof(double) * 64}};
+  if (s->opt.zero_copy_control) {
+    // staged in page-locked memory and pulled by a kernel (no copy engine: see ifx_options.zero_copy_control)
+    size_t need = 0;
+    for (const Up& u : ups) need += (u.bytes + 15) / 16 * 16;
+    if (need > s->h_stage_bytes) {
+      if (s->h_stage) cudaFreeHost(s->h_stage);
+      s->h_stage = nullptr; s->h_stage_bytes = 0;
+      IFX_CUDA(s, cudaMallocHost(&s->h_stage, need + 65536));
+      s->h_stage_bytes = need + 65536;
+    }
+    size_t off = 0;
+    for (const Up& u : ups) {
+      if (u.bytes == 0) continue;
+      std::memcpy(s->h_stage + off, u.src, u.bytes);
+      s->launches++;
+      IFX_CUDA(s, launch_copy_words(u.dst, s->h_stage + off, u.bytes, s->stream));
+      off += (u.bytes + 15) / 16 * 16;
+    }
+  } else {
+    for (const Up& u : ups)
+      if (u.bytes) IFX_CUDA(s, cudaMemcpyAsync(u.dst, u.src, u.bytes, cudaMemcpyHostToDevice, s->stream));
   }
-  IFX_CUDA(s, cudaMemcpyAsync(s->d_bbox, s->h_bbox.data(), sizeof(double) * s->h_bbox.size(), cudaMemcpyHostToDevice, s->stream));
-  IFX_CUDA(s, cudaMemcpyAsync(s->d_ub, s->h_ub.data(), sizeof(double) * 64, cudaMemcpyHostToDevice, s->stream));
-  IFX_CUDA(s, cudaMemcpyAsync(s->d_vb, s->h_vb.data(), sizeof(double) * 64, cudaMemcpyHostToDevice, s->stream));
-  IFX_CUDA(s, cudaStreamSynchronize(s->stream));      // host vectors may be reassigned by the next call
+  IFX_CUDA(s, cudaStreamSynchronize(s->stream));      // host vectors / the staging buffer may be rewritten by the next call
   s->bodies_dirty = true;
   return IFX_OK;
 }
@@ -189,9 +211,8 @@ extern "C" int ifx_iblank_update(ifx_solver* s, ifx_step_stats* st) {
   s->launches += 2;
   IFX_CUDA(s, launch_classify(L, s->M.xc, s->M.yc, B, s->celltype, s->d_rowcount, s->stream));
   IFX_CUDA(s, launch_gc_count(L, s->d_rowcount, s->d_rowstart, s->d_counters, s->stream));
-  int total = 0;
-  IFX_CUDA(s, cudaMemcpyAsync(&total, s->d_counters, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
-  IFX_CUDA(s, cudaStreamSynchronize(s->stream));
+  if ((rc = fetch_small(s, s->h_counters, s->d_counters, sizeof(int) * 4)) != IFX_OK) return rc;
+  const int total = s->h_counters[0];
   if ((rc = ensure_gc_capacity(s, total)) != IFX_OK) return rc;
   s->gc.count = total;
   s->has_gc = total > 0;
@@ -200,9 +221,8 @@ extern "C" int ifx_iblank_update(ifx_solver* s, ifx_step_stats* st) {
     IFX_CUDA(s, launch_gc_build(L, s->M.xc, s->M.yc, B, sg, s->celltype, s->d_rowstart, total,
                                 s->gc.cell, s->gc.ref_id, s->gc.body, s->gc.stencil, s->gc.stencil_ref, s->gc.w_dir,
                                 s->gc.w_neu, s->gc.bi, s->gc.ip, s->d_counters + 1, s->stream));
-    int err = 0;
-    IFX_CUDA(s, cudaMemcpyAsync(&err, s->d_counters + 1, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
-    IFX_CUDA(s, cudaStreamSynchronize(s->stream));
+    if ((rc = fetch_small(s, s->h_counters, s->d_counters, sizeof(int) * 4)) != IFX_OK) return rc;
+    const int err = s->h_counters[1];
     if (err) return fail(s, IFX_ERR_INVALID, "a ghost-cell stencil reaches more than 4 rows into (or beyond) the neighbour slab: "
                                              "use fewer ranks for this grid");
   }

@@ -236,6 +236,7 @@ cudaError_t launch_decide_exact(LoopCtl* ctl, const double* sums, const ReduceCf
 cudaError_t launch_init_vortex(const Layout& L, const double* xc, const double* yc, double* u, double* v, double* p,
                                cudaStream_t st);
 cudaError_t launch_fill_u8(uint8_t* p, size_t n, uint8_t v, cudaStream_t st);
+cudaError_t launch_copy_words(void* dst, const void* src, size_t bytes, cudaStream_t st);   // bytes: multiple of 4
 cudaError_t launch_pack_u8(const Layout& L, const uint8_t* padded, double* dense, int raw, cudaStream_t st);
 
 }  // namespace ifx

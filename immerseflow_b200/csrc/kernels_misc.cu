@@ -34,6 +34,21 @@ static __global__ void k_pack_u8(Layout L, const uint8_t* __restrict__ padded, d
   }
 }
 
+// dst <- src, 4-byte words; either side may be page-locked host memory (unified addressing: same pointer on the
+// device), which is how the zero-copy control path moves its few bytes without touching a copy engine
+static __global__ void k_copy_words(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src, size_t n) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; t < n; t += stride) dst[t] = src[t];
+}
+cudaError_t launch_copy_words(void* dst, const void* src, size_t bytes, cudaStream_t st) {
+  const size_t n = (bytes + 3) / 4;
+  if (n == 0) return cudaSuccess;
+  const unsigned blocks = (unsigned)((n + 255) / 256 > 64 ? 64 : (n + 255) / 256);
+  k_copy_words<<<blocks, 256, 0, st>>>(static_cast<uint32_t*>(dst), static_cast<const uint32_t*>(src), n);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_fill_u8(uint8_t* p, size_t n, uint8_t v, cudaStream_t st) {
   k_fill_u8<<<296, 256, 0, st>>>(p, n, v);
   return cudaGetLastError();

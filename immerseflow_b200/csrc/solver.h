@@ -46,6 +46,9 @@ struct ifx_solver {
   size_t partials_cap = 0;
   ifx::LoopCtl* ctl = nullptr;       // device
   ifx::LoopCtl* h_ctl = nullptr;     // pinned host mirror
+  int* h_counters = nullptr;         // pinned host mirror of d_counters (4 ints)
+  unsigned char* h_stage = nullptr;  // pinned staging for the body arrays (zero-copy control path)
+  size_t h_stage_bytes = 0;
   double *res_a = nullptr, *res_b = nullptr;   // reference-layout residual arrays (lazy)
   double* red_partial = nullptr;     // level-1 partials for the reference-order reduction
   double* red_out = nullptr;         // 2 doubles
@@ -102,6 +105,7 @@ namespace ifx {
 int fail(ifx_solver* s, int code, const std::string& msg);
 // shared by capi.cu and capi_full.cu
 int fetch_ctl(ifx_solver* s);
+int fetch_small(ifx_solver* s, void* host_pinned, const void* dev, size_t bytes);   // D2H of a few bytes + stream sync
 int ensure_partials(ifx_solver* s, size_t nblocks);
 int ensure_exact_buffers(ifx_solver* s);
 int exact_decide(ifx_solver* s, const ReduceCfg& rc, bool two_arrays);

@@ -100,7 +100,13 @@ typedef struct {
    * near-isotropic cells (uniform grids); on strongly stretched grids use 3 (a line smoother is not built). */
   int ppe_solver;
   double ppe_omega;         /* 0 = take ifx_input.w_PPE (an int in the reference's struct, globalVariables.cuh:26) */
-  int reserved[5];
+  /* 1: the few-byte control traffic of a step (stop flags, ghost-cell counts, marker uploads) moves through kernels
+   * that read / write page-locked host memory directly instead of through cudaMemcpyAsync.  Results are identical.
+   * For processes that run several handles at once with bulk ifx_set/get_field_async transfers in flight: a copy
+   * engine serves whole-field transfers ahead of a step's control copies and stalls it (measured on B200: a
+   * concurrent download delays a 31 ms step by 16 ms; bench.py's end-to-end pipeline sets this). */
+  int zero_copy_control;
+  int reserved[4];
 } ifx_options;
 
 /* Per-call statistics (replaces the reference's printf of "iter = %d %f %f", ADSolver.cu:369). */
