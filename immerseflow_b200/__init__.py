@@ -238,7 +238,7 @@ class ImmerseFlow:
         opt.rank, opt.nranks, opt.j_begin, opt.j_end = rank, nranks, j_begin, j_end
         opt.sweeps_per_batch = sweeps_per_batch
         opt.ppe_abs_residual = ppe_abs_residual
-        opt.ppe_solver, opt.ppe_omega = ppe_solver, ppe_omega      # 3 = red-black SOR, 4 = multigrid (full mode)
+        opt.ppe_solver, opt.ppe_omega = ppe_solver, ppe_omega      # 2 line SOR, 3 red-black SOR, 4 / 5 multigrid (full mode)
         opt.zero_copy_control = zero_copy_control
         if ad_tol is not None:
             opt.ad_tol = ad_tol

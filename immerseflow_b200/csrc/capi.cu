@@ -324,20 +324,25 @@ extern "C" int ifx_create(const ifx_input* in, const double* xf, const double* y
   if (opt.j_begin < 1 || opt.j_end > in->ny - 1 || opt.j_begin >= opt.j_end)
     return fail(nullptr, IFX_ERR_INVALID, "bad slab rows");
   if (opt.sweeps_per_batch < 1) opt.sweeps_per_batch = 64;
-  if (opt.ppe_solver == 0) opt.ppe_solver = (in->PPE_solver == 3 || in->PPE_solver == 4) ? in->PPE_solver : 1;   // 0 / 1 / 2 in the file: point Jacobi
+  // PPE_Solver of the input file (main.cu:42; the reference documents "1. Point GS, 2. Line SOR" and runs point Jacobi):
+  // the reference-compatible mode always reproduces its Jacobi; the full mode honours 2 .. 5
+  if (opt.ppe_solver == 0)
+    opt.ppe_solver = (opt.compat == IFX_COMPAT_FULL && in->PPE_solver >= 2 && in->PPE_solver <= 5) ? in->PPE_solver : 1;
   if (opt.ppe_omega == 0.0) opt.ppe_omega = (in->w_PPE != 0) ? (double)in->w_PPE : 1.0;
-  if (opt.ppe_solver != 1 && opt.ppe_solver != 3 && opt.ppe_solver != 4)
-    return fail(nullptr, IFX_ERR_INVALID, "ppe_solver: 1 (point Jacobi), 3 (red-black SOR) or 4 (multigrid); line SOR is not built");
+  if (opt.ppe_solver < 1 || opt.ppe_solver > 5)
+    return fail(nullptr, IFX_ERR_INVALID, "ppe_solver: 1 point Jacobi, 2 zebra line SOR, 3 red-black SOR, 4 multigrid (point smoother), "
+                                          "5 multigrid (line smoother)");
   if (opt.ppe_solver != 1 && opt.compat != IFX_COMPAT_FULL)
-    return fail(nullptr, IFX_ERR_INVALID, "red-black SOR / multigrid need IFX_COMPAT_FULL (the reference mode reproduces the reference's Jacobi)");
+    return fail(nullptr, IFX_ERR_INVALID, "SOR / line SOR / multigrid need IFX_COMPAT_FULL (the reference mode reproduces the reference's Jacobi)");
   if (opt.ppe_solver != 1 && !(opt.ppe_omega > 0.0 && opt.ppe_omega < 2.0))
     return fail(nullptr, IFX_ERR_INVALID, "SOR needs 0 < ppe_omega < 2");
-  if (opt.ppe_solver == 4) {
+  if (opt.ppe_solver == 4 || opt.ppe_solver == 5) {
     int lx[IFX_MG_MAX_LEVELS], ly[IFX_MG_MAX_LEVELS];
     if (mg_plan(in->nx - 2, in->ny - 2, lx, ly) < 2)
       return fail(nullptr, IFX_ERR_INVALID, "multigrid needs even cell counts (>= 4) in both directions");
-    if (opt.nranks > 1) return fail(nullptr, IFX_ERR_INVALID, "multigrid is single-GPU for now (slab runs: ppe_solver 1 or 3)");
   }
+  if ((opt.ppe_solver == 2 || opt.ppe_solver >= 4) && opt.nranks > 1)
+    return fail(nullptr, IFX_ERR_INVALID, "line SOR and multigrid are single-GPU for now (slab runs: ppe_solver 1 or 3)");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
     cudaGetLastError();
@@ -441,8 +446,10 @@ extern "C" int ifx_destroy(ifx_solver* s) {
                     s->d_counters, s->d_rowcount, s->d_rowstart};
   for (int* f : ifields) if (f) cudaFree(f);
   for (double* t : s->tables) cudaFree(t);
+  if (s->line_cp) cudaFree(s->line_cp);
+  if (s->line_dp) cudaFree(s->line_dp);
   for (int l = 1; l < s->mg_levels; l++) {
-    double* a[] = {s->mg[l].GE, s->mg[l].GN, s->mg[l].e, s->mg[l].R};
+    double* a[] = {s->mg[l].GE, s->mg[l].GN, s->mg[l].e, s->mg[l].R, s->mg[l].cp, s->mg[l].dp};
     for (double* q : a) if (q) cudaFree(q);
   }
   if (s->celltype) cudaFree(s->celltype);
@@ -957,10 +964,11 @@ static int mg_ensure(ifx_solver* s) {
     for (int l = 1; l < n; l++) {
       const size_t bytes = sizeof(double) * (size_t)(lx[l] + 2) * (ly[l] + 2);
       s->mg[l].ncx = lx[l]; s->mg[l].ncy = ly[l];
-      double** a[] = {&s->mg[l].GE, &s->mg[l].GN, &s->mg[l].e, &s->mg[l].R};
-      for (double** q : a) {
-        IFX_CUDA(s, cudaMalloc(q, bytes));
-        IFX_CUDA(s, cudaMemsetAsync(*q, 0, bytes, s->stream));
+      double** a[] = {&s->mg[l].GE, &s->mg[l].GN, &s->mg[l].e, &s->mg[l].R, &s->mg[l].cp, &s->mg[l].dp};
+      const int narr = s->opt.ppe_solver == 5 ? 6 : 4;       // Thomas scratch only for the line smoother
+      for (int q = 0; q < narr; q++) {
+        IFX_CUDA(s, cudaMalloc(a[q], bytes));
+        IFX_CUDA(s, cudaMemsetAsync(*a[q], 0, bytes, s->stream));
       }
       s->mg_levels = l + 1;          // what ifx_destroy frees if a later allocation fails
     }
@@ -972,8 +980,9 @@ static int mg_ensure(ifx_solver* s) {
       IFX_CUDA(s, cudaMemsetAsync(s->mg[l].GE, 0, bytes, s->stream));
       IFX_CUDA(s, cudaMemsetAsync(s->mg[l].GN, 0, bytes, s->stream));
       s->launches++;
-      if (l == 1) IFX_CUDA(s, launch_mg_build1(s->L, s->M, s->celltype, s->mg[1], s->stream));
-      else IFX_CUDA(s, launch_mg_coarsen(s->mg[l - 1], s->mg[l], s->stream));
+      const int lines = s->opt.ppe_solver == 5;
+      if (l == 1) IFX_CUDA(s, launch_mg_build1(s->L, s->M, s->celltype, s->mg[1], lines, s->stream));
+      else IFX_CUDA(s, launch_mg_coarsen(s->mg[l - 1], s->mg[l], lines, s->stream));
     }
     s->mg_valid = true;
   }
@@ -1084,6 +1093,130 @@ int ifx::run_ppe_multigrid(ifx_solver* s, ifx_step_stats* st) {
         if ((rc = red(0, 0, 0, false)) != IFX_OK) return rc;
         if ((rc = black()) != IFX_OK) return rc;
       }
+    }
+    K = s->h_ctl->iter;
+  }
+  s->cur_p = base;
+  IFX_CUDA(s, cudaEventRecord(s->ev[3], s->stream));
+  IFX_CUDA(s, cudaEventSynchronize(s->ev[3]));
+  if (st) {
+    st->ppe_sweeps = K;
+    st->ppe_residual = (itermax > 0) ? (s->opt.ppe_abs_residual ? s->h_ctl->res1 : s->h_ctl->res0) : 1.0;
+    st->exact_fallbacks += fallbacks;
+    cudaEventElapsedTime(&st->ms_ppe, s->ev[2], s->ev[3]);
+  }
+  return IFX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Poisson by zebra line relaxation (PPE_Solver 2: the input file's own "2. Line SOR", main.cu:42) and by the
+// line-smoothed V-cycle (PPE_Solver 5).  Semantics: orc_ppe_line_iteration / orc_mg_vcycle_lines (UNPINNED).
+// An iteration = four passes (x-lines even / odd, y-lines even / odd), each solving its lines exactly (batched Thomas,
+// one thread per line) — or one V(NU1, NU2) cycle with that iteration as the smoother on every level.  The residual
+// of iterate m-1 is evaluated, and the stop decision taken, by one launch of the bulk-copy sweep kernel in its
+// red-black instantiation with omega = 0 (it then changes nothing: its output buffer is scratch), so the certified
+// stop rule of the other solvers carries over unchanged.
+// ------------------------------------------------------------------------------------------------
+int ifx::run_ppe_lines(ifx_solver* s, ifx_step_stats* st) {
+  const Layout& L = s->L;
+  const bool mg = s->opt.ppe_solver == 5;
+  if (s->opt.nranks != 1) return fail(s, IFX_ERR_INVALID, "line relaxation is single-GPU for now");
+  if (s->kernel_variant != 4) return fail(s, IFX_ERR_INVALID, "line relaxation needs the default kernel variant");
+  const bool exact = s->opt.reduce_mode == IFX_REDUCE_REFERENCE;
+  const int itermax = s->in.PPE_itermax;
+  const int ry = rows_per_cta_for(s, 1);
+  const dim3 grid = tile_grid(s, ry, 1);
+  const size_t nblocks = (size_t)grid.x * grid.y;
+  int rc = ensure_partials(s, nblocks);
+  if (rc != IFX_OK) return rc;
+  if (exact && (rc = ensure_exact_buffers(s)) != IFX_OK) return rc;
+  if (!s->line_cp) {
+    IFX_CUDA(s, cudaMalloc(&s->line_cp, sizeof(double) * s->field_elems));
+    IFX_CUDA(s, cudaMalloc(&s->line_dp, sizeof(double) * s->field_elems));
+    IFX_CUDA(s, cudaMemsetAsync(s->line_cp, 0, sizeof(double) * s->field_elems, s->stream));
+    IFX_CUDA(s, cudaMemsetAsync(s->line_dp, 0, sizeof(double) * s->field_elems, s->stream));
+  }
+
+  IFX_CUDA(s, cudaEventRecord(s->ev[2], s->stream));
+  if (mg && (rc = mg_ensure(s)) != IFX_OK) return rc;
+  const int base = s->cur_p;          // the iterate never leaves this buffer; its partner is scratch
+  const double omega = s->opt.ppe_omega;
+  IFX_CUDA(s, cudaMemsetAsync(s->ctl, 0, sizeof(LoopCtl), s->stream));
+  int K = 0, fallbacks = 0;
+  if (itermax > 0) {
+    PpeSweepArgs pa{};
+    pa.L = L; pa.M = s->M;
+    pa.rhs = s->rhs; pa.celltype = s->celltype;
+    pa.res = s->res_a; pa.partials = s->partials; pa.ctl = s->ctl;
+    pa.rows_per_cta = ry;
+    pa.rc.itermax = itermax; pa.rc.tol = s->opt.ppe_tol; pa.rc.use_second = 0;
+    pa.rc.test_abs = s->opt.ppe_abs_residual ? 1 : 0;
+    pa.rc.certify = exact ? 0 : 1;
+    pa.rc.band = rounding_band(s, nblocks, ry);
+    pa.sor = 1; pa.sor_omega = 0.0; pa.sor_colour = 0;
+    pa.pC = s->p[base]; pa.pT = s->p[base ^ 1];
+    const int fo[1] = {4 + (base ^ 1)};
+    make_halo_ctx(s, 1, 1, fo, &pa.hx);
+    auto evaluate = [&](int eval, int decide, int force, bool write_res) -> int {   // residual of iterate `eval` (+ decision)
+      pa.rc.eval_iter = eval; pa.rc.decide = decide; pa.force = force;
+      return launch_ppe_sweep(s, pa, grid, false, write_res);
+    };
+    auto fine_lines = [&](int its) -> int {
+      for (int k = 0; k < its; k++)
+        for (int dir = 0; dir < 2; dir++)
+          for (int parity = 0; parity < 2; parity++) {
+            s->launches++;
+            IFX_CUDA(s, launch_line_pass(L, s->M, s->celltype, s->rhs, s->p[base], s->line_cp, s->line_dp, dir, parity, omega, s->stream));
+          }
+      return IFX_OK;
+    };
+    auto coarse_lines = [&](int l, int its) -> int {
+      for (int k = 0; k < its; k++)
+        for (int dir = 0; dir < 2; dir++)
+          for (int parity = 0; parity < 2; parity++) {
+            s->launches++;
+            IFX_CUDA(s, launch_mg_line_pass(s->mg[l], dir, parity, omega, s->stream));
+          }
+      return IFX_OK;
+    };
+    for (int c = 1;; c++) {
+      if ((rc = evaluate(c - 1, exact ? 0 : 1, 0, exact)) != IFX_OK) return rc;
+      if (exact && c > 1 && (rc = exact_decide(s, pa.rc, false)) != IFX_OK) return rc;
+      if ((rc = fetch_ctl(s)) != IFX_OK) return rc;
+      if (s->h_ctl->done && s->h_ctl->ambiguous) {
+        fallbacks++;
+        if ((rc = ensure_exact_buffers(s)) != IFX_OK) return rc;
+        pa.res = s->res_a;
+        if ((rc = evaluate(c - 1, 0, 1, true)) != IFX_OK) return rc;
+        if ((rc = exact_decide(s, pa.rc, false)) != IFX_OK) return rc;
+        if ((rc = fetch_ctl(s)) != IFX_OK) return rc;
+      }
+      if (s->h_ctl->done) break;
+      if (c >= itermax + 1) return fail(s, IFX_ERR_STATE, "line-relaxation loop ran past PPE_itermax without a decision");
+      if (!mg) {
+        if ((rc = fine_lines(1)) != IFX_OK) return rc;
+        continue;
+      }
+      const int Lv = s->mg_levels;
+      if ((rc = fine_lines(IFX_MG_NU1)) != IFX_OK) return rc;
+      s->launches++;
+      IFX_CUDA(s, launch_mg_restrict_fine(L, s->M, s->celltype, s->rhs, s->p[base], s->mg[1], s->stream));
+      for (int l = 1; l < Lv; l++) {
+        IFX_CUDA(s, cudaMemsetAsync(s->mg[l].e, 0, sizeof(double) * (size_t)(s->mg[l].ncx + 2) * (s->mg[l].ncy + 2), s->stream));
+        if ((rc = coarse_lines(l, l == Lv - 1 ? ifx_mg_ncoarse_lines(s->mg[l].ncx, s->mg[l].ncy) : IFX_MG_NU1)) != IFX_OK) return rc;
+        if (l < Lv - 1) {
+          s->launches++;
+          IFX_CUDA(s, launch_mg_restrict(s->mg[l], s->mg[l + 1], s->stream));
+        }
+      }
+      for (int l = Lv - 2; l >= 1; l--) {
+        s->launches++;
+        IFX_CUDA(s, launch_mg_prolong(s->mg[l + 1], s->mg[l], s->stream));
+        if ((rc = coarse_lines(l, IFX_MG_NU2)) != IFX_OK) return rc;
+      }
+      s->launches++;
+      IFX_CUDA(s, launch_mg_prolong_fine(L, s->celltype, s->mg[1], s->p[base], s->stream));
+      if ((rc = fine_lines(IFX_MG_NU2)) != IFX_OK) return rc;
     }
     K = s->h_ctl->iter;
   }

@@ -312,7 +312,9 @@ extern "C" int ifx_ppe_solve(ifx_solver* s, ifx_step_stats* st) {
   // a15: source term from the predicted velocities (their ring and ghost cells were refreshed by the predictor)
   s->launches++;
   IFX_CUDA(s, launch_ppe_rhs(s->L, s->M, s->celltype, s->d_ub, s->d_vb, s->u[s->cur_uv], s->v[s->cur_uv], s->rhs, s->stream));
-  if ((rc = (s->opt.ppe_solver == 4 ? run_ppe_multigrid(s, st) : run_ppe_loop(s, st, false))) != IFX_OK) return rc;
+  const int ps = s->opt.ppe_solver;
+  rc = ps == 4 ? run_ppe_multigrid(s, st) : (ps == 2 || ps == 5) ? run_ppe_lines(s, st) : run_ppe_loop(s, st, false);
+  if (rc != IFX_OK) return rc;
   if ((rc = full_refresh_pressure_bc(s, s->cur_p)) != IFX_OK) return rc;
   IFX_CUDA(s, cudaStreamSynchronize(s->stream));
   return IFX_OK;

@@ -26,7 +26,8 @@ static inline dim3 mg_grid(int ncx, int ncy) { return dim3((ncx + MG_BX - 1) / M
 __device__ __forceinline__ size_t cidx(int I, int J, int NX) { return (size_t)I + (size_t)J * NX; }
 
 // see dir_scale in the oracle: the factor 1/2 of a coarse face only in a direction the point smoother smooths
-__device__ __forceinline__ void mg_dir_scale(double sx, double sy, double& ax, double& ay) {
+__device__ __forceinline__ void mg_dir_scale(int lines, double sx, double sy, double& ax, double& ay) {
+  if (lines) { ax = 0.5; ay = 0.5; return; }       // alternating line relaxation smooths both directions everywhere
   ax = (sx >= 0.25 * sy) ? 0.5 : 1.0;
   ay = (sy >= 0.25 * sx) ? 0.5 : 1.0;
 }
@@ -34,7 +35,7 @@ __device__ __forceinline__ void mg_dir_scale(double sx, double sy, double& ax, d
 // ---------------------------------------------------------------------------------------------
 // level-1 conductances from the grid metrics and the cell types (oracle: build_level1)
 // ---------------------------------------------------------------------------------------------
-static __global__ void k_mg_build1(Layout L, Metrics M, const uint8_t* __restrict__ ct, MgLevel c) {
+static __global__ void k_mg_build1(Layout L, Metrics M, const uint8_t* __restrict__ ct, MgLevel c, int lines) {
   const int I = 1 + blockIdx.x * blockDim.x + threadIdx.x, J = 1 + blockIdx.y * blockDim.y + threadIdx.y;
   if (I > c.ncx || J > c.ncy) return;
   const int i = 2 * I, j = 2 * J;               // children: columns i-1, i; rows j-1, j
@@ -48,21 +49,21 @@ static __global__ void k_mg_build1(Layout L, Metrics M, const uint8_t* __restric
   }
   const double sx = ge[0] + ge[1], sy = gn[0] + gn[1];
   double ax, ay;
-  mg_dir_scale(sx, sy, ax, ay);
+  mg_dir_scale(lines, sx, sy, ax, ay);
   const size_t o = cidx(I, J, c.ncx + 2);
   c.GE[o] = ax * sx;
   c.GN[o] = ay * sy;
 }
 
 // level l+1 conductances from level l (oracle: build_coarser)
-static __global__ void k_mg_coarsen(MgLevel f, MgLevel c) {
+static __global__ void k_mg_coarsen(MgLevel f, MgLevel c, int lines) {
   const int I = 1 + blockIdx.x * blockDim.x + threadIdx.x, J = 1 + blockIdx.y * blockDim.y + threadIdx.y;
   if (I > c.ncx || J > c.ncy) return;
   const int i = 2 * I, j = 2 * J, nxl = f.ncx + 2;
   const double sx = f.GE[cidx(i, j - 1, nxl)] + f.GE[cidx(i, j, nxl)];
   const double sy = f.GN[cidx(i - 1, j, nxl)] + f.GN[cidx(i, j, nxl)];
   double ax, ay;
-  mg_dir_scale(sx, sy, ax, ay);
+  mg_dir_scale(lines, sx, sy, ax, ay);
   const size_t o = cidx(I, J, c.ncx + 2);
   c.GE[o] = ax * sx;
   c.GN[o] = ay * sy;
@@ -158,12 +159,121 @@ static __global__ void k_mg_prolong_fine(Layout L, const uint8_t* __restrict__ c
   p[o] = p[o] + c.e[cidx((i + 1) / 2, (j + 1) / 2, c.ncx + 2)];
 }
 
+
 // ---------------------------------------------------------------------------------------------
-cudaError_t launch_mg_build1(const Layout& L, const Metrics& M, const uint8_t* celltype, MgLevel c, cudaStream_t st) {
-  return IFX_KLAUNCH(k_mg_build1, mg_grid(c.ncx, c.ncy), dim3(MG_BX, MG_BY, 1), st, L, M, celltype, c);
+// Zebra line relaxation (oracle: orc_ppe_line_pass / orc_mg_line_pass).  One thread per line of the pass's parity:
+// Thomas elimination in increasing index order with one reciprocal per cell, back substitution, relaxation.  Lines
+// along y put consecutive threads on consecutive columns (coalesced); lines along x stride by a row per thread and
+// live on the L1/L2 reuse of each 128-byte line over 16 consecutive cells.  First cut: latency-bound by the
+// loop-carried division (ROADMAP: cyclic reduction per CTA), but already what makes the V-cycle contract at 0.3-0.4
+// per cycle on the reference's stretched grids, where point smoothing stalls at 0.9+.
+// ---------------------------------------------------------------------------------------------
+constexpr int LINE_THREADS = 32;
+
+static __global__ void k_line_pass(Layout L, Metrics M, const uint8_t* __restrict__ ct, const double* __restrict__ rhs,
+                                   double* p, double* __restrict__ cpw, double* __restrict__ dpw, int dir, int parity,
+                                   double omega) {
+  const int nline = dir == 0 ? L.ny : L.nx, len = dir == 0 ? L.nx : L.ny;
+  const int l = (parity ? 1 : 2) + 2 * (int)(blockIdx.x * blockDim.x + threadIdx.x);
+  if (l > nline - 2) return;
+  const size_t sk = dir == 0 ? 1 : (size_t)L.pitch;
+  const size_t o0 = dir == 0 ? lidx(L, 0, l - L.j0) : lidx(L, l, 0 - L.j0);
+  const int nxm2 = L.nx - 2, nym2 = L.ny - 2;
+  double cprev = 0.0, dprev = 0.0;
+  for (int k = 1; k < len - 1; k++) {
+    const size_t o = o0 + (size_t)k * sk;
+    const int i = dir == 0 ? k : l, j = dir == 0 ? l : k;
+    double lo = 0.0, up = 0.0, dg = 1.0, d = p[o];
+    if (ct[o] == IFX_FLUID) {
+      const bool oW = !(i == 1 || ct[o - 1] != IFX_FLUID), oE = !(i == nxm2 || ct[o + 1] != IFX_FLUID);
+      const bool oS = !(j == 1 || ct[o - L.pitch] != IFX_FLUID), oN = !(j == nym2 || ct[o + L.pitch] != IFX_FLUID);
+      const double cW = M.pp_cW[i], cE = M.pp_cE[i], cS = M.pp_cS[j], cN = M.pp_cN[j];
+      dg = -(M.pp_sx[i] + M.pp_sy[j]);                                                   // cP, PPESolver.cu:93-94
+      if (!oW) dg = dg + cW;
+      if (!oE) dg = dg + cE;
+      if (!oS) dg = dg + cS;
+      if (!oN) dg = dg + cN;
+      d = rhs[o];
+      if (dir == 0) {
+        lo = oW ? cW : 0.0; up = oE ? cE : 0.0;
+        if (oN) d = fma(-cN, p[o + L.pitch], d);
+        if (oS) d = fma(-cS, p[o - L.pitch], d);
+      } else {
+        lo = oS ? cS : 0.0; up = oN ? cN : 0.0;
+        if (oE) d = fma(-cE, p[o + 1], d);
+        if (oW) d = fma(-cW, p[o - 1], d);
+      }
+      const double piv = fma(-lo, cprev, dg);
+      if (!(piv < 0.0)) { lo = 0.0; up = 0.0; dg = 1.0; d = p[o]; }                       // isolated cell: identity row
+    }
+    const double inv = 1.0 / fma(-lo, cprev, dg);
+    cprev = up * inv;
+    dprev = fma(-lo, dprev, d) * inv;
+    cpw[o] = cprev; dpw[o] = dprev;
+  }
+  double xnext = 0.0;
+  for (int k = len - 2; k >= 1; k--) {
+    const size_t o = o0 + (size_t)k * sk;
+    const double x = fma(-cpw[o], xnext, dpw[o]);
+    xnext = x;
+    if (ct[o] == IFX_FLUID) { const double pc = p[o]; p[o] = pc + omega * (x - pc); }
+  }
 }
-cudaError_t launch_mg_coarsen(MgLevel f, MgLevel c, cudaStream_t st) {
-  return IFX_KLAUNCH(k_mg_coarsen, mg_grid(c.ncx, c.ncy), dim3(MG_BX, MG_BY, 1), st, f, c);
+
+static __global__ void k_mg_line_pass(MgLevel lv, int dir, int parity, double omega) {
+  const int NX = lv.ncx + 2, NY = lv.ncy + 2;
+  const int nline = dir == 0 ? NY : NX, len = dir == 0 ? NX : NY;
+  const int l = (parity ? 1 : 2) + 2 * (int)(blockIdx.x * blockDim.x + threadIdx.x);
+  if (l > nline - 2) return;
+  const size_t sk = dir == 0 ? 1 : (size_t)NX, sl = dir == 0 ? (size_t)NX : 1;
+  double cprev = 0.0, dprev = 0.0;
+  for (int k = 1; k < len - 1; k++) {
+    const size_t o = (size_t)l * sl + (size_t)k * sk;
+    const double ge = lv.GE[o], gw = lv.GE[o - 1], gn = lv.GN[o], gs = lv.GN[o - NX];
+    const double D = (ge + gw) + (gn + gs);
+    double lo = 0.0, up = 0.0, dg = 1.0, d = lv.e[o];
+    if (D > 0.0) {
+      dg = -D;
+      d = lv.R[o];
+      if (dir == 0) { lo = gw; up = ge; d = fma(-gn, lv.e[o + NX], d); d = fma(-gs, lv.e[o - NX], d); }
+      else { lo = gs; up = gn; d = fma(-ge, lv.e[o + 1], d); d = fma(-gw, lv.e[o - 1], d); }
+      const double piv = fma(-lo, cprev, dg);
+      if (!(piv < 0.0)) { lo = 0.0; up = 0.0; dg = 1.0; d = lv.e[o]; }
+    }
+    const double inv = 1.0 / fma(-lo, cprev, dg);
+    cprev = up * inv;
+    dprev = fma(-lo, dprev, d) * inv;
+    lv.cp[o] = cprev; lv.dp[o] = dprev;
+  }
+  double xnext = 0.0;
+  for (int k = len - 2; k >= 1; k--) {
+    const size_t o = (size_t)l * sl + (size_t)k * sk;
+    const double x = fma(-lv.cp[o], xnext, lv.dp[o]);
+    xnext = x;
+    const double D = (lv.GE[o] + lv.GE[o - 1]) + (lv.GN[o] + lv.GN[o - NX]);
+    if (D > 0.0) { const double ec = lv.e[o]; lv.e[o] = ec + omega * (x - ec); }
+  }
+}
+
+static inline dim3 line_grid(int nline) {      // lines of one parity among 1 .. nline-2
+  const int n = (nline - 2 + 1) / 2;
+  return dim3((n + LINE_THREADS - 1) / LINE_THREADS, 1, 1);
+}
+
+// ---------------------------------------------------------------------------------------------
+cudaError_t launch_line_pass(const Layout& L, const Metrics& M, const uint8_t* celltype, const double* rhs, double* p,
+                             double* cpw, double* dpw, int dir, int parity, double omega, cudaStream_t st) {
+  return IFX_KLAUNCH(k_line_pass, line_grid(dir == 0 ? L.ny : L.nx), dim3(LINE_THREADS, 1, 1), st, L, M, celltype, rhs, p, cpw,
+                     dpw, dir, parity, omega);
+}
+cudaError_t launch_mg_line_pass(MgLevel l, int dir, int parity, double omega, cudaStream_t st) {
+  return IFX_KLAUNCH(k_mg_line_pass, line_grid(dir == 0 ? l.ncy + 2 : l.ncx + 2), dim3(LINE_THREADS, 1, 1), st, l, dir, parity, omega);
+}
+cudaError_t launch_mg_build1(const Layout& L, const Metrics& M, const uint8_t* celltype, MgLevel c, int lines, cudaStream_t st) {
+  return IFX_KLAUNCH(k_mg_build1, mg_grid(c.ncx, c.ncy), dim3(MG_BX, MG_BY, 1), st, L, M, celltype, c, lines);
+}
+cudaError_t launch_mg_coarsen(MgLevel f, MgLevel c, int lines, cudaStream_t st) {
+  return IFX_KLAUNCH(k_mg_coarsen, mg_grid(c.ncx, c.ncy), dim3(MG_BX, MG_BY, 1), st, f, c, lines);
 }
 cudaError_t launch_mg_restrict_fine(const Layout& L, const Metrics& M, const uint8_t* celltype, const double* rhs,
                                     const double* p, MgLevel c, cudaStream_t st) {

@@ -39,7 +39,7 @@ struct Args {
   bool reference_log = false;
   bool exact = false;
   bool checkpoints = false;      // write restart files every Write_Interval steps and after the last one
-  int ppe_solver = 0;            // 0: PPE_Solver of inputs.txt; 1 point Jacobi; 3 red-black SOR; 4 multigrid (full mode)
+  int ppe_solver = 0;            // 0: PPE_Solver of inputs.txt; 1 point Jacobi; 2 line SOR; 3 red-black SOR; 4, 5 multigrid (full mode)
   double ppe_omega = 0.0;        // 0: w-PPE of inputs.txt (an integer there)
   std::string restart;           // explicit restart file (default when Restart != 0: <results>/restart.<Restart_Time>.ifx)
   int device = 0;
@@ -68,7 +68,7 @@ static void usage() {
       "immerseflow [--input FILE] [--xgrid FILE] [--ygrid FILE] [--stretched] [--results DIR]\n"
       "            [--mode reference|full] [--bodies FILE] [--steps N] [--write-every-step]\n"
       "            [--reference-log] [--exact-reduction] [--checkpoints] [--restart FILE] [--device K]\n"
-      "            [--ppe-solver 1|3|4] [--ppe-omega W] [--bc-u W,E,S,N] [--bc-v W,E,S,N] [--ic vortex|zero|uniform:U,V]\n"
+      "            [--ppe-solver 1..5] [--ppe-omega W] [--bc-u W,E,S,N] [--bc-v W,E,S,N] [--ic vortex|zero|uniform:U,V]\n"
       "            [--forces FILE] [--probes FILE --probe-out FILE]\n"
       "  defaults reproduce the reference binary run from src/: ../inputs/inputs.txt, ../inputs/{x,y}grid.dat2,\n"
       "  tmax predictor steps, ../results/{final_results,uc,vc}.dat.  --stretched picks ../inputs/{x,y}grid.dat.\n"
@@ -76,7 +76,9 @@ static void usage() {
       "  --checkpoints a restart file <results>/restart.<step, 7 digits>.ifx goes with them.  `Restart 1 T` in inputs.txt\n"
       "  (or --restart FILE) continues from <results>/restart.<T>.ifx: steps T+1 .. tmax, bit-identical to an unbroken run.\n"
       "  --ppe-solver 3 (or PPE_Solver 3 in inputs.txt; full mode): red-black SOR with factor --ppe-omega / w-PPE.\n"
-      "  --ppe-solver 4: geometric multigrid V(2,2) cycles (even cell counts; PPE_itermax then counts cycles).\n"
+      "  --ppe-solver 2 (PPE_Solver 2, the input file's \"Line SOR\"): zebra line relaxation, factor --ppe-omega / w-PPE.\n"
+      "  --ppe-solver 4 / 5: geometric multigrid V(2,2) cycles smoothed by red-black SOR (uniform grids) / by line\n"
+      "  relaxation (stretched grids); even cell counts; PPE_itermax then counts cycles.\n"
       "  --bodies FILE (full mode): `nbodies`, then per body a line `nmarkers ub vb [ax ay f]` and nmarkers lines `x y`\n"
       "  (counter-clockwise).  A body translates as x0 + ub t + ax sin(2 pi f t) (same in y); moving bodies are\n"
       "  re-classified every step.\n"

@@ -14,11 +14,15 @@
 // iterations on the coarsest level: max(32, its cell count), at most 2048 (a grid like 200 x 120 stops at 25 x 15)
 inline int ifx_mg_ncoarse(int ncx, int ncy) { const int n = ncx * ncy; return n < 32 ? 32 : (n > 2048 ? 2048 : n); }
 
+// line-relaxation iterations on the coarsest level of the line-smoothed cycle: an eighth of its cells, within [8, 512]
+inline int ifx_mg_ncoarse_lines(int ncx, int ncy) { const int n = ncx * ncy / 8; return n < 8 ? 8 : (n > 512 ? 512 : n); }
+
 namespace ifx {
 
 struct MgLevel {
   int ncx, ncy;               // cells (without the ghost ring)
   double* GE; double* GN; double* e; double* R;
+  double* cp; double* dp;     // Thomas scratch of the line smoother (PPE_Solver 5 only, else null)
 };
 
 // levels for an ncx x ncy grid: halve while both counts are even and >= 4.  Returns the number of levels incl. level 0.
@@ -34,13 +38,19 @@ inline int mg_plan(int ncx, int ncy, int* lx, int* ly) {
 
 // kernels_mg.cu.  The GE / GN arrays of the target level must be zero-filled before the two build launches
 // (their ghost ring is never written).
-cudaError_t launch_mg_build1(const Layout& L, const Metrics& M, const uint8_t* celltype, MgLevel c, cudaStream_t st);
-cudaError_t launch_mg_coarsen(MgLevel f, MgLevel c, cudaStream_t st);
+// lines = 1: hierarchy of the line-smoothed cycle (every coarse face scaled by 1/2, see the oracle's dir_scale)
+cudaError_t launch_mg_build1(const Layout& L, const Metrics& M, const uint8_t* celltype, MgLevel c, int lines, cudaStream_t st);
+cudaError_t launch_mg_coarsen(MgLevel f, MgLevel c, int lines, cudaStream_t st);
 cudaError_t launch_mg_restrict_fine(const Layout& L, const Metrics& M, const uint8_t* celltype, const double* rhs,
                                     const double* p, MgLevel c, cudaStream_t st);
 cudaError_t launch_mg_smooth(MgLevel l, int colour, double omega, cudaStream_t st);
 cudaError_t launch_mg_restrict(MgLevel f, MgLevel c, cudaStream_t st);
 cudaError_t launch_mg_prolong(MgLevel c, MgLevel f, cudaStream_t st);
 cudaError_t launch_mg_prolong_fine(const Layout& L, const uint8_t* celltype, MgLevel c, double* p, cudaStream_t st);
+// zebra line relaxation (PPE_Solver 2; smoother of PPE_Solver 5): one pass over the lines of one parity, dir 0 = lines
+// along x (rows), dir 1 = along y (columns).  cpw / dpw: scratch fields in the layout of p.
+cudaError_t launch_line_pass(const Layout& L, const Metrics& M, const uint8_t* celltype, const double* rhs, double* p,
+                             double* cpw, double* dpw, int dir, int parity, double omega, cudaStream_t st);
+cudaError_t launch_mg_line_pass(MgLevel l, int dir, int parity, double omega, cudaStream_t st);
 
 }  // namespace ifx

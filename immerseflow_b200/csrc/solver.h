@@ -88,6 +88,7 @@ struct ifx_solver {
   int mg_levels = 0;
   ifx::MgLevel mg[IFX_MG_MAX_LEVELS] = {};
   bool mg_valid = false;             // the conductances match the current cell types (cleared by ifx_iblank_update)
+  double *line_cp = nullptr, *line_dp = nullptr;   // fine-level Thomas scratch of the line relaxation (PPE_Solver 2, 5)
 
   int kernel_variant = 4;            // 1: register-rolled direct loads (kernels_ad.cu / kernels_ppe.cu, reference mode only)
                                      // 4: bulk-copy row pipeline, lean interior path (kernels_v4.cu, default)
@@ -116,6 +117,7 @@ void fill_bc(const ifx_solver* s, double* two_u, double* two_v);
 int run_ad_loop(ifx_solver* s, ifx_step_stats* st, bool full);
 int run_ppe_loop(ifx_solver* s, ifx_step_stats* st, bool laplace_ref);
 int run_ppe_multigrid(ifx_solver* s, ifx_step_stats* st);
+int run_ppe_lines(ifx_solver* s, ifx_step_stats* st);
 int full_refresh_velocity_bc(ifx_solver* s, int buf);
 int full_refresh_pressure_bc(ifx_solver* s, int buf);
 // slabs

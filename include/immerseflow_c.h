@@ -94,10 +94,14 @@ typedef struct {
                                DESIGN.md's next step for launch-bound small grids */
   /* Poisson iteration (IFX_COMPAT_FULL).  The reference documents PPE_Solver "1. Point GS, 2. Line
    * SOR" and w-PPE in inputs.txt, parses them (main.cu:42) and always runs point Jacobi.  0 = take
-   * ifx_input.PPE_solver; 1 = point Jacobi (the reference's sweep); 3 = red-black SOR with factor ppe_omega;
-   * 4 = geometric multigrid, V(2,2) cycles smoothed by red-black SOR with factor ppe_omega (single GPU, even cell
-   * counts; an "iteration" of PPE_itermax / ifx_step_stats.ppe_sweeps is then one V-cycle).  Effective on
-   * near-isotropic cells (uniform grids); on strongly stretched grids use 3 (a line smoother is not built). */
+   * ifx_input.PPE_solver (full mode; the reference-compatible mode always runs the reference's Jacobi);
+   *   1 = point Jacobi (the reference's sweep);
+   *   2 = zebra line SOR with factor ppe_omega: x-lines even / odd, y-lines even / odd, each line solved exactly;
+   *   3 = red-black SOR with factor ppe_omega;
+   *   4 = geometric multigrid, V(2,2) cycles smoothed by red-black SOR — for near-isotropic cells (uniform grids);
+   *   5 = geometric multigrid smoothed by the line relaxation of 2 — for the stretched grids the reference ships.
+   * 4 and 5 need even cell counts; an "iteration" of PPE_itermax / ifx_step_stats.ppe_sweeps is then one V-cycle.
+   * 2, 4 and 5 are single-GPU for now. */
   int ppe_solver;
   double ppe_omega;         /* 0 = take ifx_input.w_PPE (an int in the reference's struct, globalVariables.cuh:26) */
   /* 1: the few-byte control traffic of a step (stop flags, ghost-cell counts, marker uploads) moves through kernels

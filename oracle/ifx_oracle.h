@@ -172,6 +172,7 @@ void orc_full_probe(orc_full* s, int npts, const double* px, const double* py, d
 #define ORC_MG_NU1 2
 #define ORC_MG_NU2 2
 #define ORC_MG_NCOARSE 0    /* 0: max(32, cells of the coarsest level), at most 2048 (orc_mg_ncoarse) */
+int orc_mg_ncoarse_lines(int ncx, int ncy);
 typedef struct orc_mg orc_mg;
 int orc_mg_plan(int ncx, int ncy, int* lx, int* ly);
 int orc_mg_ncoarse(int ncx, int ncy);
@@ -192,7 +193,20 @@ void orc_mg_coarse_cycle(orc_mg* m, int nu1, int nu2, int ncoarse, double omega)
 void orc_mg_vcycle(orc_mg* m, int nx, int ny, const double* dx, const double* dy, const double* cP, const double* cxm,
                    const double* cxp, const double* cym, const double* cyp, const unsigned char* ct, const double* rhs,
                    int nu1, int nu2, int ncoarse, double omega, double* p, double* pT);
-/* the multigrid hierarchy of the last orc_full_poisson call with solver 4 (NULL before) */
+/* zebra line relaxation (PPE_Solver 2) and the line-smoothed V-cycle (PPE_Solver 5) */
+orc_mg* orc_mg_create2(int nx, int ny, const double* dx, const double* dy, const unsigned char* celltype, int lines);
+void orc_ppe_line_pass(int nx, int ny, const double* cP, const double* cxm, const double* cxp, const double* cym,
+                       const double* cyp, const unsigned char* ct, const double* rhs, int dir, int parity, double omega,
+                       double* p, double* cpw, double* dpw);
+void orc_ppe_line_iteration(int nx, int ny, const double* cP, const double* cxm, const double* cxp, const double* cym,
+                            const double* cyp, const unsigned char* ct, const double* rhs, double omega, double* p,
+                            double* cpw, double* dpw);
+void orc_mg_line_pass(int NX, int NY, const double* GE, const double* GN, const double* R, int dir, int parity,
+                      double omega, double* e, double* cpw, double* dpw);
+void orc_mg_vcycle_lines(orc_mg* m, int nx, int ny, const double* dx, const double* dy, const double* cP, const double* cxm,
+                         const double* cxp, const double* cym, const double* cyp, const unsigned char* ct, const double* rhs,
+                         int nu1, int nu2, int ncoarse, double omega, double* p, double* cpw, double* dpw);
+/* the multigrid hierarchy of the last orc_full_poisson call with solver 4 / 5 (NULL before) */
 const orc_mg* orc_full_mg(const orc_full* s);
 void orc_full_correct(orc_full* s);
 void orc_full_step(orc_full* s, double* stats);

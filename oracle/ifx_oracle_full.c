@@ -592,12 +592,17 @@ int orc_full_poisson(orc_full* s, double* stats) {
   memcpy(pT, pc, N * 8);
   double R = 1.0, Rabs = 1.0;
   int iter = 0;
-  if (s->ppe_solver == 4) {          /* an "iteration" is one V-cycle */
+  if (s->ppe_solver == 4 || s->ppe_solver == 5) {          /* an "iteration" is one V-cycle */
     orc_mg_destroy(s->mg);
-    s->mg = orc_mg_create(nx, ny, s->dx, s->dy, s->celltype);
+    s->mg = orc_mg_create2(nx, ny, s->dx, s->dy, s->celltype, s->ppe_solver == 5);
   }
   while ((s->ppe_abs ? Rabs : R) > s->ppe_tol && iter < s->PPE_itermax) {
-    if (s->ppe_solver == 4) {
+    if (s->ppe_solver == 2) {          /* zebra line relaxation; scratch: pT and res */
+      orc_ppe_line_iteration(nx, ny, cP, cxm, cxp, cym, cyp, s->celltype, s->rhs, s->w_ppe, pc, pT, res);
+    } else if (s->ppe_solver == 5) {
+      orc_mg_vcycle_lines(s->mg, nx, ny, s->dx, s->dy, cP, cxm, cxp, cym, cyp, s->celltype, s->rhs, s->mg_nu1, s->mg_nu2,
+                          s->mg_ncoarse, s->w_ppe, pc, pT, res);
+    } else if (s->ppe_solver == 4) {
       orc_mg_vcycle(s->mg, nx, ny, s->dx, s->dy, cP, cxm, cxp, cym, cyp, s->celltype, s->rhs, s->mg_nu1, s->mg_nu2,
                     s->mg_ncoarse, s->w_ppe, pc, pT);
     } else if (s->ppe_solver == 3) {       /* red-black SOR: two half-sweeps, the iterate ends up where it started */

@@ -35,7 +35,8 @@
  * direction's in this cell; across a weakly coupled direction the error after smoothing is not smooth, the factor
  * 1/2 would over-correct (the cycle diverges on the reference's stretched grids, cell aspect ratios up to 27),
  * so the plain sum (Galerkin for piecewise-constant transfer) is kept there. */
-static void dir_scale(double sx, double sy, double* ax, double* ay) {
+static void dir_scale(int lines, double sx, double sy, double* ax, double* ay) {
+  if (lines) { *ax = 0.5; *ay = 0.5; return; }      /* alternating line relaxation smooths both directions everywhere */
   *ax = (sx >= 0.25 * sy) ? 0.5 : 1.0;
   *ay = (sy >= 0.25 * sx) ? 0.5 : 1.0;
 }
@@ -46,7 +47,9 @@ struct orc_mg {
   /* levels >= 1: ghost-inclusive arrays (ncx+2) x (ncy+2); GE(I,J) = conductance of the east face of (I,J),
    * GN(I,J) = north face; faces on or outside the grid boundary are 0 */
   double *GE[ORC_MG_MAX_LEVELS], *GN[ORC_MG_MAX_LEVELS], *e[ORC_MG_MAX_LEVELS], *R[ORC_MG_MAX_LEVELS];
+  double *cpw[ORC_MG_MAX_LEVELS], *dpw[ORC_MG_MAX_LEVELS];      /* Thomas scratch of the line smoother */
 };
+orc_mg* orc_mg_create2(int nx, int ny, const double* dx, const double* dy, const unsigned char* celltype, int lines);
 
 int orc_mg_plan(int ncx, int ncy, int* lx, int* ly) {
   int n = 1;
@@ -67,8 +70,17 @@ int orc_mg_ncoarse(int ncx, int ncy) {
   return n;
 }
 
+/* line-relaxation iterations on the coarsest level of PPE_Solver 5: an eighth of its cell count, within [8, 512]
+ * (8 for the 2 x 2 .. 7 x 7 levels that even-friendly grids end on; 180 for the 45 x 32 of the shipped 180 x 128 case) */
+int orc_mg_ncoarse_lines(int ncx, int ncy) {
+  int n = ncx * ncy / 8;
+  if (n < 8) n = 8;
+  if (n > 512) n = 512;
+  return n;
+}
+
 /* level-1 conductances from the fine geometry and cell types */
-static void build_level1(int nx, int ny, const double* dx, const double* dy, const unsigned char* ct, int NX,
+static void build_level1(int lines, int nx, int ny, const double* dx, const double* dy, const unsigned char* ct, int NX,
                          int NY, double* GE, double* GN) {
   memset(GE, 0, sizeof(double) * (size_t)NX * NY);
   memset(GN, 0, sizeof(double) * (size_t)NX * NY);
@@ -84,13 +96,13 @@ static void build_level1(int nx, int ny, const double* dx, const double* dy, con
         if (j <= ny - 3 && IS_FLUID(ct[ID(ii, j, nx)]) && IS_FLUID(ct[ID(ii, j + 1, nx)]))
           gn[k] = (2.0 * dx[ID(ii, j, nx)]) / (dy[ID(ii, j, nx)] + dy[ID(ii, j + 1, nx)]);
       }
-      double ax, ay; dir_scale(ge[0] + ge[1], gn[0] + gn[1], &ax, &ay);
+      double ax, ay; dir_scale(lines, ge[0] + ge[1], gn[0] + gn[1], &ax, &ay);
       GE[ID(I, J, NX)] = ax * (ge[0] + ge[1]);
       GN[ID(I, J, NX)] = ay * (gn[0] + gn[1]);
     }
 }
 
-static void build_coarser(int nxl, const double* GEf, const double* GNf, int NX, int NY, double* GE, double* GN) {
+static void build_coarser(int lines, int nxl, const double* GEf, const double* GNf, int NX, int NY, double* GE, double* GN) {
   memset(GE, 0, sizeof(double) * (size_t)NX * NY);
   memset(GN, 0, sizeof(double) * (size_t)NX * NY);
 #pragma omp parallel for
@@ -98,28 +110,33 @@ static void build_coarser(int nxl, const double* GEf, const double* GNf, int NX,
     for (int I = 1; I < NX - 1; I++) {
       const int i = 2 * I, j = 2 * J;
       const double sx = GEf[ID(i, j - 1, nxl)] + GEf[ID(i, j, nxl)], sy = GNf[ID(i - 1, j, nxl)] + GNf[ID(i, j, nxl)];
-      double ax, ay; dir_scale(sx, sy, &ax, &ay);
+      double ax, ay; dir_scale(lines, sx, sy, &ax, &ay);
       GE[ID(I, J, NX)] = ax * sx;
       GN[ID(I, J, NX)] = ay * sy;
     }
 }
 
 orc_mg* orc_mg_create(int nx, int ny, const double* dx, const double* dy, const unsigned char* celltype) {
+  return orc_mg_create2(nx, ny, dx, dy, celltype, 0);
+}
+/* lines = 1: hierarchy for the line-smoothed cycle (coarse faces always scaled by 1/2) + line scratch per level */
+orc_mg* orc_mg_create2(int nx, int ny, const double* dx, const double* dy, const unsigned char* celltype, int lines) {
   orc_mg* m = (orc_mg*)calloc(1, sizeof(orc_mg));
   m->nlevels = orc_mg_plan(nx - 2, ny - 2, m->ncx, m->ncy);
   for (int l = 1; l < m->nlevels; l++) {
     const size_t n = (size_t)(m->ncx[l] + 2) * (m->ncy[l] + 2);
     m->GE[l] = (double*)calloc(n, 8); m->GN[l] = (double*)calloc(n, 8);
     m->e[l] = (double*)calloc(n, 8); m->R[l] = (double*)calloc(n, 8);
-    if (l == 1) build_level1(nx, ny, dx, dy, celltype, m->ncx[1] + 2, m->ncy[1] + 2, m->GE[1], m->GN[1]);
-    else build_coarser(m->ncx[l - 1] + 2, m->GE[l - 1], m->GN[l - 1], m->ncx[l] + 2, m->ncy[l] + 2, m->GE[l], m->GN[l]);
+    m->cpw[l] = (double*)calloc(n, 8); m->dpw[l] = (double*)calloc(n, 8);
+    if (l == 1) build_level1(lines, nx, ny, dx, dy, celltype, m->ncx[1] + 2, m->ncy[1] + 2, m->GE[1], m->GN[1]);
+    else build_coarser(lines, m->ncx[l - 1] + 2, m->GE[l - 1], m->GN[l - 1], m->ncx[l] + 2, m->ncy[l] + 2, m->GE[l], m->GN[l]);
   }
   return m;
 }
 
 void orc_mg_destroy(orc_mg* m) {
   if (!m) return;
-  for (int l = 1; l < m->nlevels; l++) { free(m->GE[l]); free(m->GN[l]); free(m->e[l]); free(m->R[l]); }
+  for (int l = 1; l < m->nlevels; l++) { free(m->GE[l]); free(m->GN[l]); free(m->e[l]); free(m->R[l]); free(m->cpw[l]); free(m->dpw[l]); }
   free(m);
 }
 
@@ -269,4 +286,150 @@ void orc_mg_vcycle(orc_mg* m, int nx, int ny, const double* dx, const double* dy
     orc_ppe_sor_halfsweep(nx, ny, cP, cxm, cxp, cym, cyp, ct, rhs, 0, omega, p, pT);
     orc_ppe_sor_halfsweep(nx, ny, cP, cxm, cxp, cym, cyp, ct, rhs, 1, omega, pT, p);
   }
+}
+
+/* =================================================================================================
+ * Zebra line relaxation ("line-SOR via batched Thomas solves"; the input file's own
+ * "PPE_Solver ... 2. Line SOR", parsed at main.cu:42 and never used by the reference).  UNPINNED.
+ *
+ * One pass relaxes every second grid line (lines of index parity `parity`) simultaneously: along the line the
+ * Poisson equation of orc_ppe_sweep_general is solved exactly for all its cells at once (tridiagonal system,
+ * Thomas algorithm in increasing index order), the two neighbouring lines — of the other parity, untouched by the
+ * pass — on the right-hand side; then p <- p + omega (p* - p).  dir 0: lines along x (rows j), dir 1: lines along y
+ * (columns i).  Closed faces (grid boundary, non-fluid neighbour) drop out of the stencil, which moves their
+ * coefficient onto the diagonal (p_nb := p_C); non-fluid cells are identity rows, so a line falls into
+ * independent fluid segments by itself.  Row of cell k of the line:   lo_k x_{k-1} + dg_k x_k + up_k x_{k+1} = d_k.
+ * Elimination with one reciprocal per cell:
+ *     inv_k = 1 / (dg_k - lo_k cp_{k-1}),  cp_k = up_k inv_k,  dp_k = (d_k - lo_k dp_{k-1}) inv_k,
+ *     x_k = dp_k - cp_k x_{k+1}.
+ * A cell whose pivot is not negative (an isolated fluid cell: dg = 0) keeps its value.
+ * cpw / dpw: scratch of nx*ny doubles each (every line uses its own cells' slots).
+ * An iteration of PPE_Solver 2 is four passes: x-lines even, x-lines odd, y-lines even, y-lines odd.
+ * ================================================================================================= */
+void orc_ppe_line_pass(int nx, int ny, const double* cP, const double* cxm, const double* cxp, const double* cym,
+                       const double* cyp, const unsigned char* ct, const double* rhs, int dir, int parity, double omega,
+                       double* p, double* cpw, double* dpw) {
+  const int nline = dir == 0 ? ny : nx, len = dir == 0 ? nx : ny;
+  const int sk = dir == 0 ? 1 : nx;            /* stride along the line */
+  const int sl = dir == 0 ? nx : 1;            /* stride across lines */
+#pragma omp parallel for
+  for (int l = 1; l < nline - 1; l++) {
+    if ((l & 1) != parity) continue;
+    double cprev = 0.0, dprev = 0.0;
+    for (int k = 1; k < len - 1; k++) {
+      const int id = l * sl + k * sk;
+      double lo = 0.0, up = 0.0, dg = 1.0, d = p[id];
+      if (IS_FLUID(ct[id])) {
+        const int i = id % nx, j = id / nx;
+        const int oW = !(i == 1 || !IS_FLUID(ct[id - 1])), oE = !(i == nx - 2 || !IS_FLUID(ct[id + 1]));
+        const int oS = !(j == 1 || !IS_FLUID(ct[id - nx])), oN = !(j == ny - 2 || !IS_FLUID(ct[id + nx]));
+        /* diagonal = cP + coefficients of the closed faces (p_nb := p_C), added in the order W, E, S, N */
+        dg = cP[id];
+        if (!oW) dg = dg + cxm[id];
+        if (!oE) dg = dg + cxp[id];
+        if (!oS) dg = dg + cym[id];
+        if (!oN) dg = dg + cyp[id];
+        d = rhs[id];
+        if (dir == 0) {
+          lo = oW ? cxm[id] : 0.0; up = oE ? cxp[id] : 0.0;
+          if (oN) d = fma(-cyp[id], p[id + nx], d);
+          if (oS) d = fma(-cym[id], p[id - nx], d);
+        } else {
+          lo = oS ? cym[id] : 0.0; up = oN ? cyp[id] : 0.0;
+          if (oE) d = fma(-cxp[id], p[id + 1], d);
+          if (oW) d = fma(-cxm[id], p[id - 1], d);
+        }
+        const double piv = fma(-lo, cprev, dg);
+        if (!(piv < 0.0)) { lo = 0.0; up = 0.0; dg = 1.0; d = p[id]; }      /* isolated: identity row */
+      }
+      const double inv = 1.0 / fma(-lo, cprev, dg);
+      cprev = up * inv;
+      dprev = fma(-lo, dprev, d) * inv;
+      cpw[id] = cprev; dpw[id] = dprev;
+    }
+    double xnext = 0.0;
+    for (int k = len - 2; k >= 1; k--) {
+      const int id = l * sl + k * sk;
+      const double x = fma(-cpw[id], xnext, dpw[id]);
+      xnext = x;
+      if (IS_FLUID(ct[id])) p[id] = p[id] + omega * (x - p[id]);
+    }
+  }
+}
+
+void orc_ppe_line_iteration(int nx, int ny, const double* cP, const double* cxm, const double* cxp, const double* cym,
+                            const double* cyp, const unsigned char* ct, const double* rhs, double omega, double* p,
+                            double* cpw, double* dpw) {
+  for (int dir = 0; dir < 2; dir++)
+    for (int parity = 0; parity < 2; parity++)
+      orc_ppe_line_pass(nx, ny, cP, cxm, cxp, cym, cyp, ct, rhs, dir, parity, omega, p, cpw, dpw);
+}
+
+/* the same on a coarse level: row of cell k:  G_lo e_{k-1} - D e_k + G_up e_{k+1} = R - (other direction's G e_nb) */
+void orc_mg_line_pass(int NX, int NY, const double* GE, const double* GN, const double* R, int dir, int parity,
+                      double omega, double* e, double* cpw, double* dpw) {
+  const int nline = dir == 0 ? NY : NX, len = dir == 0 ? NX : NY;
+  const int sk = dir == 0 ? 1 : NX, sl = dir == 0 ? NX : 1;
+#pragma omp parallel for
+  for (int l = 1; l < nline - 1; l++) {
+    if ((l & 1) != parity) continue;
+    double cprev = 0.0, dprev = 0.0;
+    for (int k = 1; k < len - 1; k++) {
+      const int id = l * sl + k * sk;
+      const double ge = GE[id], gw = GE[id - 1], gn = GN[id], gs = GN[id - NX];
+      const double D = (ge + gw) + (gn + gs);
+      double lo = 0.0, up = 0.0, dg = 1.0, d = e[id];
+      if (D > 0.0) {
+        dg = -D;
+        d = R[id];
+        if (dir == 0) { lo = gw; up = ge; d = fma(-gn, e[id + NX], d); d = fma(-gs, e[id - NX], d); }
+        else { lo = gs; up = gn; d = fma(-ge, e[id + 1], d); d = fma(-gw, e[id - 1], d); }
+        const double piv = fma(-lo, cprev, dg);
+        if (!(piv < 0.0)) { lo = 0.0; up = 0.0; dg = 1.0; d = e[id]; }
+      }
+      const double inv = 1.0 / fma(-lo, cprev, dg);
+      cprev = up * inv;
+      dprev = fma(-lo, dprev, d) * inv;
+      cpw[id] = cprev; dpw[id] = dprev;
+    }
+    double xnext = 0.0;
+    for (int k = len - 2; k >= 1; k--) {
+      const int id = l * sl + k * sk;
+      const double x = fma(-cpw[id], xnext, dpw[id]);
+      xnext = x;
+      const double D = (GE[id] + GE[id - 1]) + (GN[id] + GN[id - NX]);
+      if (D > 0.0) e[id] = e[id] + omega * (x - e[id]);
+    }
+  }
+}
+
+/* V(nu1, nu2) cycle smoothed by alternating zebra line relaxation on every level (PPE_Solver 5).  Hierarchy from
+ * orc_mg_create2(..., lines = 1).  cpw / dpw: fine-level scratch of nx*ny doubles each. */
+static void mg_lines(orc_mg* m, int l, int its, double omega) {
+  const int NX = m->ncx[l] + 2, NY = m->ncy[l] + 2;
+  for (int k = 0; k < its; k++)
+    for (int dir = 0; dir < 2; dir++)
+      for (int parity = 0; parity < 2; parity++)
+        orc_mg_line_pass(NX, NY, m->GE[l], m->GN[l], m->R[l], dir, parity, omega, m->e[l], m->cpw[l], m->dpw[l]);
+}
+
+void orc_mg_vcycle_lines(orc_mg* m, int nx, int ny, const double* dx, const double* dy, const double* cP, const double* cxm,
+                         const double* cxp, const double* cym, const double* cyp, const unsigned char* ct, const double* rhs,
+                         int nu1, int nu2, int ncoarse, double omega, double* p, double* cpw, double* dpw) {
+  const int L = m->nlevels;
+  for (int k = 0; k < nu1; k++) orc_ppe_line_iteration(nx, ny, cP, cxm, cxp, cym, cyp, ct, rhs, omega, p, cpw, dpw);
+  orc_mg_restrict_fine(nx, ny, dx, dy, cP, cxm, cxp, cym, cyp, ct, rhs, p, m->ncx[1] + 2, m->ncy[1] + 2, m->R[1]);
+  for (int l = 1; l < L; l++) {
+    const int NX = m->ncx[l] + 2, NY = m->ncy[l] + 2;
+    memset(m->e[l], 0, 8 * (size_t)NX * NY);
+    mg_lines(m, l, (l == L - 1) ? (ncoarse > 0 ? ncoarse : orc_mg_ncoarse_lines(m->ncx[l], m->ncy[l])) : nu1, omega);
+    if (l < L - 1)
+      orc_mg_restrict(NX, m->GE[l], m->GN[l], m->R[l], m->e[l], m->ncx[l + 1] + 2, m->ncy[l + 1] + 2, m->R[l + 1]);
+  }
+  for (int l = L - 2; l >= 1; l--) {
+    orc_mg_prolong(m->ncx[l] + 2, m->ncy[l] + 2, m->GE[l], m->GN[l], m->ncx[l + 1] + 2, m->e[l + 1], m->e[l]);
+    mg_lines(m, l, nu2, omega);
+  }
+  orc_mg_prolong_fine(nx, ny, ct, m->ncx[1] + 2, m->e[1], p);
+  for (int k = 0; k < nu2; k++) orc_ppe_line_iteration(nx, ny, cP, cxm, cxp, cym, cyp, ct, rhs, omega, p, cpw, dpw);
 }

@@ -16,13 +16,23 @@ static Metrics metrics_of(const double* const* t) {
   return M;
 }
 static Layout layout_of(int nx, int ny, int pitch) { return Layout{nx, ny, pitch, ny, 0, 1, ny - 1}; }
-static MgLevel level_of(int ncx, int ncy, double* GE, double* GN, double* e, double* R) { return MgLevel{ncx, ncy, GE, GN, e, R}; }
-
-void shim_mg_build1(int nx, int ny, int pitch, const double* const* tables, const uint8_t* ct, int ncx, int ncy, double* GE, double* GN) {
-  launch_mg_build1(layout_of(nx, ny, pitch), metrics_of(tables), ct, level_of(ncx, ncy, GE, GN, nullptr, nullptr), nullptr);
+static MgLevel level_of(int ncx, int ncy, double* GE, double* GN, double* e, double* R, double* cp = nullptr, double* dp = nullptr) {
+  return MgLevel{ncx, ncy, GE, GN, e, R, cp, dp};
 }
-void shim_mg_coarsen(int fx, int fy, double* fGE, double* fGN, int cx, int cy, double* GE, double* GN) {
-  launch_mg_coarsen(level_of(fx, fy, fGE, fGN, nullptr, nullptr), level_of(cx, cy, GE, GN, nullptr, nullptr), nullptr);
+
+void shim_mg_build1(int nx, int ny, int pitch, const double* const* tables, const uint8_t* ct, int ncx, int ncy, double* GE, double* GN, int lines) {
+  launch_mg_build1(layout_of(nx, ny, pitch), metrics_of(tables), ct, level_of(ncx, ncy, GE, GN, nullptr, nullptr), lines, nullptr);
+}
+void shim_mg_coarsen(int fx, int fy, double* fGE, double* fGN, int cx, int cy, double* GE, double* GN, int lines) {
+  launch_mg_coarsen(level_of(fx, fy, fGE, fGN, nullptr, nullptr), level_of(cx, cy, GE, GN, nullptr, nullptr), lines, nullptr);
+}
+void shim_line_pass(int nx, int ny, int pitch, const double* const* tables, const uint8_t* ct, const double* rhs, double* p,
+                    double* cpw, double* dpw, int dir, int parity, double omega) {
+  launch_line_pass(layout_of(nx, ny, pitch), metrics_of(tables), ct, rhs, p, cpw, dpw, dir, parity, omega, nullptr);
+}
+void shim_mg_line_pass(int ncx, int ncy, double* GE, double* GN, double* e, double* R, double* cp, double* dp, int dir, int parity,
+                       double omega) {
+  launch_mg_line_pass(level_of(ncx, ncy, GE, GN, e, R, cp, dp), dir, parity, omega, nullptr);
 }
 void shim_mg_restrict_fine(int nx, int ny, int pitch, const double* const* tables, const uint8_t* ct, const double* rhs,
                            const double* p, int ncx, int ncy, double* R) {

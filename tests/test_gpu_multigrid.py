@@ -62,3 +62,28 @@ def test_multigrid_needs_even_cell_counts_and_full_mode():
     inp = ifx.make_input(64, 64, 1e-3, 150.0)
     with pytest.raises(ifx.IfxError, match="IFX_COMPAT_FULL"):
         ifx.ImmerseFlow(inp, ifx.uniform_faces(64, 1.0), ifx.uniform_faces(64, 1.0), ppe_solver=4)
+
+
+@pytest.mark.parametrize("reduce_mode", [ifx.IFX_REDUCE_FUSED, ifx.IFX_REDUCE_REFERENCE])
+@pytest.mark.parametrize("solver,omega,ncx,ncy,itermax", [(5, 1.0, 96, 64, 40), (5, 1.0, 180, 128, 40), (2, 1.8, 32, 24, 3000)])
+def test_line_relaxation_and_line_smoothed_multigrid_match_oracle(solver, omega, ncx, ncy, itermax, reduce_mode):
+    """PPE_Solver 2 (zebra line SOR, the input file's own "2. Line SOR") and 5 (V-cycle smoothed by it) on a stretched grid
+    with two bodies: pressure bit-exact after every step, identical iteration counts."""
+    xf, yf = orc.stretched_faces(ncx, 4.0, 1.03), orc.stretched_faces(ncy, 2.0, 1.03)
+    g, o = pair(xf, yf, 2e-3, 100.0, 25, itermax, ppe_tol=1e-5, reduce_mode=reduce_mode, ppe_solver=solver, ppe_omega=omega)
+    o.set_ppe_solver(solver, omega)
+    with g:
+        bodies = [orc.circle_markers(1.5, 1.0, 0.3, 64), orc.ellipse_markers(2.6, 0.9, 0.35, 0.12, 0.5, 50)]
+        g.set_bodies(bodies); o.set_bodies(bodies)
+        g.initializeData()
+        n = g.field_size("u")
+        g.set("u", np.ones(n)); g.set("v", np.zeros(n)); g.set("p", np.zeros(n))
+        o.set("u", np.ones(n)); o.set("v", np.zeros(n)); o.update_ib()
+        for step in range(2):
+            st = g.step(); so = o.step()
+            assert (st.ad_iters, st.ppe_sweeps) == (int(so[0]), int(so[3])), f"step {step}"
+            assert_same_fields(g, o, tag=f"step {step}")
+            assert st.ppe_sweeps < itermax and st.ppe_residual <= 1e-5, (st.ppe_sweeps, st.ppe_residual)
+            if reduce_mode == ifx.IFX_REDUCE_REFERENCE:
+                assert st.ppe_residual == so[4]
+    o.close()

@@ -77,11 +77,12 @@ def u8(a):
     return a.ctypes.data_as(C.POINTER(C.c_ubyte))
 
 
+@pytest.mark.parametrize("lines", [0, 1])
 @pytest.mark.parametrize("ncx,ncy,stretched,bodies", [(64, 32, False, False), (96, 48, True, True), (40, 72, True, True),
                                                       (50, 50, False, True)])
-def test_mg_kernels_match_oracle_bit_for_bit(shim, ncx, ncy, stretched, bodies):
+def test_mg_kernels_match_oracle_bit_for_bit(shim, ncx, ncy, stretched, bodies, lines):
     L = orc.lib()
-    L.orc_mg_create.restype = C.c_void_p
+    L.orc_mg_create2.restype = C.c_void_p
     g, ct = case(ncx, ncy, stretched, bodies)
     nx, ny, N = g.nx, g.ny, g.nx * g.ny
     lx, ly = (C.c_int * 16)(), (C.c_int * 16)()
@@ -89,7 +90,7 @@ def test_mg_kernels_match_oracle_bit_for_bit(shim, ncx, ncy, stretched, bodies):
     lx2, ly2 = (C.c_int * 16)(), (C.c_int * 16)()
     assert shim.shim_mg_plan(ncx, ncy, lx2, ly2) == nlev and list(lx) == list(lx2) and list(ly) == list(ly2)
     assert nlev >= 2
-    mg = C.c_void_p(L.orc_mg_create(nx, ny, P(g.dx), P(g.dy), u8(ct)))
+    mg = C.c_void_p(L.orc_mg_create2(nx, ny, P(g.dx), P(g.dy), u8(ct), lines))
     tabs, tarr = tables_1d(g)
     ctp = pad(ct, nx, ny, dtype=np.uint8, fill=1)
     pitch = pitch_of(nx)
@@ -105,9 +106,9 @@ def test_mg_kernels_match_oracle_bit_for_bit(shim, ncx, ncy, stretched, bodies):
         n = (lx[l] + 2) * (ly[l] + 2)
         GE[l], GN[l] = np.zeros(n), np.zeros(n)
         if l == 1:
-            shim.shim_mg_build1(nx, ny, pitch, tarr, u8(ctp), lx[1], ly[1], P(GE[1]), P(GN[1]))
+            shim.shim_mg_build1(nx, ny, pitch, tarr, u8(ctp), lx[1], ly[1], P(GE[1]), P(GN[1]), lines)
         else:
-            shim.shim_mg_coarsen(lx[l - 1], ly[l - 1], P(GE[l - 1]), P(GN[l - 1]), lx[l], ly[l], P(GE[l]), P(GN[l]))
+            shim.shim_mg_coarsen(lx[l - 1], ly[l - 1], P(GE[l - 1]), P(GN[l - 1]), lx[l], ly[l], P(GE[l]), P(GN[l]), lines)
         assert np.array_equal(GE[l], olevel(l, 0)) and np.array_equal(GN[l], olevel(l, 1)), f"level {l}"
         if bodies and l == 1:
             assert (GE[1].reshape(ly[1] + 2, lx[1] + 2)[1:-1, 1:-2] == 0).any()      # closed faces made it to level 1
@@ -138,6 +139,11 @@ def test_mg_kernels_match_oracle_bit_for_bit(shim, ncx, ncy, stretched, bodies):
             L.orc_mg_smooth(NX, NY, P(GE[l]), P(GN[l]), P(R), colour, omega, P(e_o))
             shim.shim_mg_smooth(lx[l], ly[l], P(GE[l]), P(GN[l]), P(e_s), P(R), colour, omega)
             assert np.array_equal(e_o, e_s), f"smooth level {l} colour {colour}"
+        sc_o = [np.zeros(n), np.zeros(n)]; sc_s = [np.zeros(n), np.zeros(n)]
+        for d, par in ((0, 0), (0, 1), (1, 0), (1, 1), (0, 0)):      # zebra line relaxation
+            L.orc_mg_line_pass(NX, NY, P(GE[l]), P(GN[l]), P(R), d, par, omega, P(e_o), P(sc_o[0]), P(sc_o[1]))
+            shim.shim_mg_line_pass(lx[l], ly[l], P(GE[l]), P(GN[l]), P(e_s), P(R), P(sc_s[0]), P(sc_s[1]), d, par, omega)
+            assert np.array_equal(e_o, e_s), f"line pass level {l} dir {d} parity {par}"
         if l + 1 < nlev:
             nc = (lx[l + 1] + 2) * (ly[l + 1] + 2)
             Rc_o, Rc_s = np.zeros(nc), np.zeros(nc)
@@ -148,6 +154,22 @@ def test_mg_kernels_match_oracle_bit_for_bit(shim, ncx, ncy, stretched, bodies):
             L.orc_mg_prolong(NX, NY, P(GE[l]), P(GN[l]), lx[l + 1] + 2, P(ec), P(e_o))
             shim.shim_mg_prolong(lx[l + 1], ly[l + 1], P(ec), lx[l], ly[l], P(GE[l]), P(GN[l]), P(e_s))
             assert np.array_equal(e_o, e_s), f"prolong level {l}"
+
+    # ---- zebra line relaxation on the fine level (in place; scratch in the layout of p)
+    p_o = p.copy(); pp2 = pad(p, nx, ny)
+    so = [np.zeros(N), np.zeros(N)]; ss = [np.zeros(pp2.size), np.zeros(pp2.size)]
+    for d, par in ((0, 0), (0, 1), (1, 0), (1, 1), (1, 0), (0, 1)):
+        L.orc_ppe_line_pass(nx, ny, P(cP), P(cxm), P(cxp), P(cym), P(cyp), u8(ct), P(rhs), d, par, omega, P(p_o), P(so[0]), P(so[1]))
+        shim.shim_line_pass(nx, ny, pitch, tarr, u8(ctp), P(rp), P(pp2), P(ss[0]), P(ss[1]), d, par, omega)
+        assert np.array_equal(unpad(pp2, nx, ny), p_o), f"fine line pass dir {d} parity {par}"
+    assert not np.array_equal(p_o, p)
+    if bodies:      # a line solve is exact along the line: the residual of the rows just relaxed with omega = 1 vanishes there
+        q_o = p.copy()
+        L.orc_ppe_line_pass(nx, ny, P(cP), P(cxm), P(cxp), P(cym), P(cyp), u8(ct), P(rhs), 0, 1, C.c_double(1.0), P(q_o), P(so[0]), P(so[1]))
+        res = np.zeros(N); scratch = np.zeros(N)
+        L.orc_ppe_sweep_general(nx, ny, P(cP), P(cxm), P(cxp), P(cym), P(cyp), u8(ct), P(rhs), P(q_o), P(scratch), P(res))
+        r2 = res.reshape(ny, nx)
+        assert np.abs(r2[1:-1:2, :]).max() < 1e-9 * np.abs(cP).max() and np.abs(r2[2:-1:2, :]).max() > 1e-3
 
     # ---- prolongation to the fine level
     e1 = rng.standard_normal(n1)
