@@ -446,10 +446,10 @@ extern "C" int ifx_destroy(ifx_solver* s) {
                     s->d_counters, s->d_rowcount, s->d_rowstart};
   for (int* f : ifields) if (f) cudaFree(f);
   for (double* t : s->tables) cudaFree(t);
-  if (s->line_cp) cudaFree(s->line_cp);
-  if (s->line_dp) cudaFree(s->line_dp);
+  for (double* q : s->line_f) if (q) cudaFree(q);
   for (int l = 1; l < s->mg_levels; l++) {
-    double* a[] = {s->mg[l].GE, s->mg[l].GN, s->mg[l].e, s->mg[l].R, s->mg[l].cp, s->mg[l].dp};
+    double* a[] = {s->mg[l].GE, s->mg[l].GN, s->mg[l].e, s->mg[l].R, s->mg[l].inv_x, s->mg[l].cp_x, s->mg[l].inv_y, s->mg[l].cp_y,
+                   s->mg[l].dp};
     for (double* q : a) if (q) cudaFree(q);
   }
   if (s->celltype) cudaFree(s->celltype);
@@ -964,8 +964,9 @@ static int mg_ensure(ifx_solver* s) {
     for (int l = 1; l < n; l++) {
       const size_t bytes = sizeof(double) * (size_t)(lx[l] + 2) * (ly[l] + 2);
       s->mg[l].ncx = lx[l]; s->mg[l].ncy = ly[l];
-      double** a[] = {&s->mg[l].GE, &s->mg[l].GN, &s->mg[l].e, &s->mg[l].R, &s->mg[l].cp, &s->mg[l].dp};
-      const int narr = s->opt.ppe_solver == 5 ? 6 : 4;       // Thomas scratch only for the line smoother
+      double** a[] = {&s->mg[l].GE, &s->mg[l].GN, &s->mg[l].e, &s->mg[l].R, &s->mg[l].inv_x, &s->mg[l].cp_x, &s->mg[l].inv_y,
+                      &s->mg[l].cp_y, &s->mg[l].dp};
+      const int narr = s->opt.ppe_solver == 5 ? 9 : 4;       // line-elimination storage only for the line smoother
       for (int q = 0; q < narr; q++) {
         IFX_CUDA(s, cudaMalloc(a[q], bytes));
         IFX_CUDA(s, cudaMemsetAsync(*a[q], 0, bytes, s->stream));
@@ -983,6 +984,11 @@ static int mg_ensure(ifx_solver* s) {
       const int lines = s->opt.ppe_solver == 5;
       if (l == 1) IFX_CUDA(s, launch_mg_build1(s->L, s->M, s->celltype, s->mg[1], lines, s->stream));
       else IFX_CUDA(s, launch_mg_coarsen(s->mg[l - 1], s->mg[l], lines, s->stream));
+      if (lines) {                   // eliminate the lines of both directions once for this set of cell types
+        s->launches += 2;
+        IFX_CUDA(s, launch_mg_line_factor(s->mg[l], 0, s->stream));
+        IFX_CUDA(s, launch_mg_line_factor(s->mg[l], 1, s->stream));
+      }
     }
     s->mg_valid = true;
   }
@@ -1130,15 +1136,22 @@ int ifx::run_ppe_lines(ifx_solver* s, ifx_step_stats* st) {
   int rc = ensure_partials(s, nblocks);
   if (rc != IFX_OK) return rc;
   if (exact && (rc = ensure_exact_buffers(s)) != IFX_OK) return rc;
-  if (!s->line_cp) {
-    IFX_CUDA(s, cudaMalloc(&s->line_cp, sizeof(double) * s->field_elems));
-    IFX_CUDA(s, cudaMalloc(&s->line_dp, sizeof(double) * s->field_elems));
-    IFX_CUDA(s, cudaMemsetAsync(s->line_cp, 0, sizeof(double) * s->field_elems, s->stream));
-    IFX_CUDA(s, cudaMemsetAsync(s->line_dp, 0, sizeof(double) * s->field_elems, s->stream));
+  if (!s->line_f[4]) {
+    for (double*& q : s->line_f) {
+      IFX_CUDA(s, cudaMalloc(&q, sizeof(double) * s->field_elems));
+      IFX_CUDA(s, cudaMemsetAsync(q, 0, sizeof(double) * s->field_elems, s->stream));
+    }
+    s->line_factor_valid = false;
   }
 
   IFX_CUDA(s, cudaEventRecord(s->ev[2], s->stream));
   if (mg && (rc = mg_ensure(s)) != IFX_OK) return rc;
+  if (!s->line_factor_valid) {        // the elimination of every line, once per set of cell types
+    s->launches += 2;
+    IFX_CUDA(s, launch_line_factor(L, s->M, s->celltype, 0, s->line_f[0], s->line_f[1], s->stream));
+    IFX_CUDA(s, launch_line_factor(L, s->M, s->celltype, 1, s->line_f[2], s->line_f[3], s->stream));
+    s->line_factor_valid = true;
+  }
   const int base = s->cur_p;          // the iterate never leaves this buffer; its partner is scratch
   const double omega = s->opt.ppe_omega;
   IFX_CUDA(s, cudaMemsetAsync(s->ctl, 0, sizeof(LoopCtl), s->stream));
@@ -1166,7 +1179,8 @@ int ifx::run_ppe_lines(ifx_solver* s, ifx_step_stats* st) {
         for (int dir = 0; dir < 2; dir++)
           for (int parity = 0; parity < 2; parity++) {
             s->launches++;
-            IFX_CUDA(s, launch_line_pass(L, s->M, s->celltype, s->rhs, s->p[base], s->line_cp, s->line_dp, dir, parity, omega, s->stream));
+            IFX_CUDA(s, launch_line_solve(L, s->M, s->celltype, s->rhs, s->p[base], s->line_f[2 * dir], s->line_f[2 * dir + 1],
+                                          s->line_f[4], dir, parity, omega, s->stream));
           }
       return IFX_OK;
     };
@@ -1175,7 +1189,7 @@ int ifx::run_ppe_lines(ifx_solver* s, ifx_step_stats* st) {
         for (int dir = 0; dir < 2; dir++)
           for (int parity = 0; parity < 2; parity++) {
             s->launches++;
-            IFX_CUDA(s, launch_mg_line_pass(s->mg[l], dir, parity, omega, s->stream));
+            IFX_CUDA(s, launch_mg_line_solve(s->mg[l], dir, parity, omega, s->stream));
           }
       return IFX_OK;
     };

@@ -228,6 +228,7 @@ extern "C" int ifx_iblank_update(ifx_solver* s, ifx_step_stats* st) {
   }
   s->bodies_dirty = false;
   s->mg_valid = false;             // so did the open faces the coarse-level conductances are made of
+  s->line_factor_valid = false;    // and the matrices of the line relaxation
   s->faces_valid = false;          // closed faces moved with the bodies
   s->state_bc_fresh = false;
   IFX_CUDA(s, cudaEventRecord(s->ev[7], s->stream));

@@ -161,29 +161,39 @@ static __global__ void k_mg_prolong_fine(Layout L, const uint8_t* __restrict__ c
 
 
 // ---------------------------------------------------------------------------------------------
-// Zebra line relaxation (oracle: orc_ppe_line_pass / orc_mg_line_pass).  One thread per line of the pass's parity:
-// Thomas elimination in increasing index order with one reciprocal per cell, back substitution, relaxation.  Lines
-// along y put consecutive threads on consecutive columns (coalesced); lines along x stride by a row per thread and
-// live on the L1/L2 reuse of each 128-byte line over 16 consecutive cells.  First cut: latency-bound by the
-// loop-carried division (ROADMAP: cyclic reduction per CTA), but already what makes the V-cycle contract at 0.3-0.4
-// per cycle on the reference's stretched grids, where point smoothing stalls at 0.9+.
+// Zebra line relaxation (oracle: orc_ppe_line_pass / orc_mg_line_pass).  One thread per line, Thomas elimination in
+// increasing index order with one reciprocal per cell, back substitution, relaxation — the oracle's operations in the
+// oracle's order, split in two kernels:
+//   * FACTOR (once per set of cell types): the elimination of the matrix itself — inv_k = 1/(dg_k - lo_k cp_{k-1}),
+//     cp_k = up_k inv_k — depends on the geometry and the cell types only, so it is stored per direction and
+//     reused by every pass of every iteration (same values, computed once: the loop-carried division, ~200 cycles
+//     per cell, leaves the hot loop).  A real row has inv < 0 (the pivot is negative); identity rows (non-fluid
+//     cells, isolated fluid cells) are stored as inv = 1, cp = 0, which is exactly what the oracle's arithmetic
+//     makes of them — so the sign of inv tells the solve kernel which kind of row it is.
+//   * SOLVE (every pass): right-hand side, dp_k = (d_k - lo_k dp_{k-1}) inv_k, back substitution, relaxation.  The
+//     loads of LINE_U consecutive cells are issued before the dependent chain of those cells runs (the first cut,
+//     one load-use round trip per cell with a warp or two per SM, was latency-bound at ~1 us per cell:
+//     profiles/r1_line_mg_bench_first_cut.jsonl).
+// Lines along y put consecutive threads on consecutive columns (coalesced); lines along x stride by a row per thread
+// and rely on each 128-byte line serving 16 consecutive cells of the same thread from L1/L2.
 // ---------------------------------------------------------------------------------------------
 constexpr int LINE_THREADS = 32;
+constexpr int LINE_U = 8;
 
-static __global__ void k_line_pass(Layout L, Metrics M, const uint8_t* __restrict__ ct, const double* __restrict__ rhs,
-                                   double* p, double* __restrict__ cpw, double* __restrict__ dpw, int dir, int parity,
-                                   double omega) {
-  const int nline = dir == 0 ? L.ny : L.nx, len = dir == 0 ? L.nx : L.ny;
-  const int l = (parity ? 1 : 2) + 2 * (int)(blockIdx.x * blockDim.x + threadIdx.x);
+template <int DIR>
+static __global__ void k_line_factor(Layout L, Metrics M, const uint8_t* __restrict__ ct, double* __restrict__ inv_a,
+                                     double* __restrict__ cp_a) {
+  const int nline = DIR == 0 ? L.ny : L.nx, len = DIR == 0 ? L.nx : L.ny;
+  const int l = 1 + (int)(blockIdx.x * blockDim.x + threadIdx.x);
   if (l > nline - 2) return;
-  const size_t sk = dir == 0 ? 1 : (size_t)L.pitch;
-  const size_t o0 = dir == 0 ? lidx(L, 0, l - L.j0) : lidx(L, l, 0 - L.j0);
+  const size_t sk = DIR == 0 ? 1 : (size_t)L.pitch;
+  const size_t o0 = DIR == 0 ? lidx(L, 0, l - L.j0) : lidx(L, l, 0 - L.j0);
   const int nxm2 = L.nx - 2, nym2 = L.ny - 2;
-  double cprev = 0.0, dprev = 0.0;
+  double cprev = 0.0;
   for (int k = 1; k < len - 1; k++) {
     const size_t o = o0 + (size_t)k * sk;
-    const int i = dir == 0 ? k : l, j = dir == 0 ? l : k;
-    double lo = 0.0, up = 0.0, dg = 1.0, d = p[o];
+    const int i = DIR == 0 ? k : l, j = DIR == 0 ? l : k;
+    double lo = 0.0, up = 0.0, dg = 1.0;
     if (ct[o] == IFX_FLUID) {
       const bool oW = !(i == 1 || ct[o - 1] != IFX_FLUID), oE = !(i == nxm2 || ct[o + 1] != IFX_FLUID);
       const bool oS = !(j == 1 || ct[o - L.pitch] != IFX_FLUID), oN = !(j == nym2 || ct[o + L.pitch] != IFX_FLUID);
@@ -193,62 +203,160 @@ static __global__ void k_line_pass(Layout L, Metrics M, const uint8_t* __restric
       if (!oE) dg = dg + cE;
       if (!oS) dg = dg + cS;
       if (!oN) dg = dg + cN;
-      d = rhs[o];
-      if (dir == 0) {
-        lo = oW ? cW : 0.0; up = oE ? cE : 0.0;
-        if (oN) d = fma(-cN, p[o + L.pitch], d);
-        if (oS) d = fma(-cS, p[o - L.pitch], d);
-      } else {
-        lo = oS ? cS : 0.0; up = oN ? cN : 0.0;
-        if (oE) d = fma(-cE, p[o + 1], d);
-        if (oW) d = fma(-cW, p[o - 1], d);
-      }
+      if (DIR == 0) { lo = oW ? cW : 0.0; up = oE ? cE : 0.0; }
+      else { lo = oS ? cS : 0.0; up = oN ? cN : 0.0; }
       const double piv = fma(-lo, cprev, dg);
-      if (!(piv < 0.0)) { lo = 0.0; up = 0.0; dg = 1.0; d = p[o]; }                       // isolated cell: identity row
+      if (!(piv < 0.0)) { lo = 0.0; up = 0.0; dg = 1.0; }                                 // isolated cell: identity row
     }
     const double inv = 1.0 / fma(-lo, cprev, dg);
     cprev = up * inv;
-    dprev = fma(-lo, dprev, d) * inv;
-    cpw[o] = cprev; dpw[o] = dprev;
-  }
-  double xnext = 0.0;
-  for (int k = len - 2; k >= 1; k--) {
-    const size_t o = o0 + (size_t)k * sk;
-    const double x = fma(-cpw[o], xnext, dpw[o]);
-    xnext = x;
-    if (ct[o] == IFX_FLUID) { const double pc = p[o]; p[o] = pc + omega * (x - pc); }
+    inv_a[o] = inv; cp_a[o] = cprev;
   }
 }
 
-static __global__ void k_mg_line_pass(MgLevel lv, int dir, int parity, double omega) {
-  const int NX = lv.ncx + 2, NY = lv.ncy + 2;
-  const int nline = dir == 0 ? NY : NX, len = dir == 0 ? NX : NY;
+template <int DIR>
+static __global__ void k_line_solve(Layout L, Metrics M, const uint8_t* __restrict__ ct, const double* __restrict__ rhs,
+                                    double* p, const double* __restrict__ inv_a, const double* __restrict__ cp_a,
+                                    double* __restrict__ dpw, int parity, double omega) {
+  const int nline = DIR == 0 ? L.ny : L.nx, len = DIR == 0 ? L.nx : L.ny;
   const int l = (parity ? 1 : 2) + 2 * (int)(blockIdx.x * blockDim.x + threadIdx.x);
   if (l > nline - 2) return;
-  const size_t sk = dir == 0 ? 1 : (size_t)NX, sl = dir == 0 ? (size_t)NX : 1;
-  double cprev = 0.0, dprev = 0.0;
+  const size_t sk = DIR == 0 ? 1 : (size_t)L.pitch;       // along the line
+  const size_t sc = DIR == 0 ? (size_t)L.pitch : 1;       // across: the neighbouring lines (other parity, untouched)
+  const size_t o0 = DIR == 0 ? lidx(L, 0, l - L.j0) : lidx(L, l, 0 - L.j0);
+  // the cross-direction stencil of the whole line: north / south for x-lines, east / west for y-lines
+  const bool hi_inside = DIR == 0 ? (l != L.ny - 2) : (l != L.nx - 2), lo_inside = (l != 1);
+  const double c_hi = DIR == 0 ? M.pp_cN[l] : M.pp_cE[l], c_lo = DIR == 0 ? M.pp_cS[l] : M.pp_cW[l];
+  const double* __restrict__ c_along = DIR == 0 ? M.pp_cW : M.pp_cS;      // the sub-diagonal coefficient, by cell index
+  double dprev = 0.0;
+  bool prev_fluid = false;                                 // cell k-1 of the line (k = 1: the ring, a closed face)
+  for (int k0 = 1; k0 < len - 1; k0 += LINE_U) {
+    const int n = min(LINE_U, len - 1 - k0);
+    double v_inv[LINE_U], v_rhs[LINE_U], v_phi[LINE_U], v_plo[LINE_U], v_pc[LINE_U], v_ca[LINE_U];
+    uint8_t v_ct[LINE_U], v_chi[LINE_U], v_clo[LINE_U];
+#pragma unroll
+    for (int u = 0; u < LINE_U; u++) {
+      if (u < n) {
+        const size_t o = o0 + (size_t)(k0 + u) * sk;
+        v_inv[u] = inv_a[o]; v_rhs[u] = rhs[o]; v_pc[u] = p[o];
+        v_phi[u] = p[o + sc]; v_plo[u] = p[o - sc];
+        v_ct[u] = ct[o]; v_chi[u] = ct[o + sc]; v_clo[u] = ct[o - sc];
+        v_ca[u] = c_along[k0 + u];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < LINE_U; u++) {
+      if (u < n) {
+        const int k = k0 + u;
+        const bool fluid = v_ct[u] == IFX_FLUID;
+        const bool real_row = v_inv[u] < 0.0;              // fluid and not isolated (see FACTOR)
+        double lo = 0.0, d = v_pc[u];
+        if (real_row) {
+          lo = (k != 1 && prev_fluid) ? v_ca[u] : 0.0;
+          d = v_rhs[u];
+          if (hi_inside && v_chi[u] == IFX_FLUID) d = fma(-c_hi, v_phi[u], d);
+          if (lo_inside && v_clo[u] == IFX_FLUID) d = fma(-c_lo, v_plo[u], d);
+        }
+        dprev = fma(-lo, dprev, d) * v_inv[u];
+        dpw[o0 + (size_t)k * sk] = dprev;
+        prev_fluid = fluid;
+      }
+    }
+  }
+  double xnext = 0.0;
+  for (int k1 = len - 2; k1 >= 1; k1 -= LINE_U) {
+    const int n = min(LINE_U, k1);
+    double v_cp[LINE_U], v_dp[LINE_U], v_pc[LINE_U];
+    uint8_t v_ct[LINE_U];
+#pragma unroll
+    for (int u = 0; u < LINE_U; u++) {
+      if (u < n) {
+        const size_t o = o0 + (size_t)(k1 - u) * sk;
+        v_cp[u] = cp_a[o]; v_dp[u] = dpw[o]; v_pc[u] = p[o]; v_ct[u] = ct[o];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < LINE_U; u++) {
+      if (u < n) {
+        const double x = fma(-v_cp[u], xnext, v_dp[u]);
+        xnext = x;
+        if (v_ct[u] == IFX_FLUID) p[o0 + (size_t)(k1 - u) * sk] = v_pc[u] + omega * (x - v_pc[u]);
+      }
+    }
+  }
+}
+
+template <int DIR>
+static __global__ void k_mg_line_factor(MgLevel lv) {
+  const int NX = lv.ncx + 2, NY = lv.ncy + 2;
+  const int nline = DIR == 0 ? NY : NX, len = DIR == 0 ? NX : NY;
+  const int l = 1 + (int)(blockIdx.x * blockDim.x + threadIdx.x);
+  if (l > nline - 2) return;
+  const size_t sk = DIR == 0 ? 1 : (size_t)NX, sl = DIR == 0 ? (size_t)NX : 1;
+  double* __restrict__ inv_a = DIR == 0 ? lv.inv_x : lv.inv_y;
+  double* __restrict__ cp_a = DIR == 0 ? lv.cp_x : lv.cp_y;
+  double cprev = 0.0;
   for (int k = 1; k < len - 1; k++) {
     const size_t o = (size_t)l * sl + (size_t)k * sk;
     const double ge = lv.GE[o], gw = lv.GE[o - 1], gn = lv.GN[o], gs = lv.GN[o - NX];
     const double D = (ge + gw) + (gn + gs);
-    double lo = 0.0, up = 0.0, dg = 1.0, d = lv.e[o];
+    double lo = 0.0, up = 0.0, dg = 1.0;
     if (D > 0.0) {
       dg = -D;
-      d = lv.R[o];
-      if (dir == 0) { lo = gw; up = ge; d = fma(-gn, lv.e[o + NX], d); d = fma(-gs, lv.e[o - NX], d); }
-      else { lo = gs; up = gn; d = fma(-ge, lv.e[o + 1], d); d = fma(-gw, lv.e[o - 1], d); }
+      if (DIR == 0) { lo = gw; up = ge; } else { lo = gs; up = gn; }
       const double piv = fma(-lo, cprev, dg);
-      if (!(piv < 0.0)) { lo = 0.0; up = 0.0; dg = 1.0; d = lv.e[o]; }
+      if (!(piv < 0.0)) { lo = 0.0; up = 0.0; dg = 1.0; }
     }
     const double inv = 1.0 / fma(-lo, cprev, dg);
     cprev = up * inv;
-    dprev = fma(-lo, dprev, d) * inv;
-    lv.cp[o] = cprev; lv.dp[o] = dprev;
+    inv_a[o] = inv; cp_a[o] = cprev;
+  }
+}
+
+template <int DIR>
+static __global__ void k_mg_line_solve(MgLevel lv, int parity, double omega) {
+  const int NX = lv.ncx + 2, NY = lv.ncy + 2;
+  const int nline = DIR == 0 ? NY : NX, len = DIR == 0 ? NX : NY;
+  const int l = (parity ? 1 : 2) + 2 * (int)(blockIdx.x * blockDim.x + threadIdx.x);
+  if (l > nline - 2) return;
+  const size_t sk = DIR == 0 ? 1 : (size_t)NX, sl = DIR == 0 ? (size_t)NX : 1, sc = sl;
+  const double* __restrict__ inv_a = DIR == 0 ? lv.inv_x : lv.inv_y;
+  const double* __restrict__ cp_a = DIR == 0 ? lv.cp_x : lv.cp_y;
+  // conductances towards the next / previous cell ACROSS the line and towards the previous cell ALONG it:
+  //   x-lines: across = GN(o), GN(o - NX), along = GE(o - 1);   y-lines: across = GE(o), GE(o - 1), along = GN(o - NX)
+  const double* __restrict__ g_across = DIR == 0 ? lv.GN : lv.GE;
+  const double* __restrict__ g_along = DIR == 0 ? lv.GE : lv.GN;
+  double dprev = 0.0;
+  for (int k0 = 1; k0 < len - 1; k0 += LINE_U) {
+    const int n = min(LINE_U, len - 1 - k0);
+    double v_inv[LINE_U], v_R[LINE_U], v_ehi[LINE_U], v_elo[LINE_U], v_ec[LINE_U], v_ghi[LINE_U], v_glo[LINE_U], v_ga[LINE_U];
+#pragma unroll
+    for (int u = 0; u < LINE_U; u++) {
+      if (u < n) {
+        const size_t o = (size_t)l * sl + (size_t)(k0 + u) * sk;
+        v_inv[u] = inv_a[o]; v_R[u] = lv.R[o]; v_ec[u] = lv.e[o];
+        v_ehi[u] = lv.e[o + sc]; v_elo[u] = lv.e[o - sc];
+        v_ghi[u] = g_across[o]; v_glo[u] = g_across[o - sc]; v_ga[u] = g_along[o - sk];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < LINE_U; u++) {
+      if (u < n) {
+        double lo = 0.0, d = v_ec[u];
+        if (v_inv[u] < 0.0) {                             // active cell that is not isolated along the line
+          lo = v_ga[u];
+          d = fma(-v_ghi[u], v_ehi[u], v_R[u]);
+          d = fma(-v_glo[u], v_elo[u], d);
+        }
+        dprev = fma(-lo, dprev, d) * v_inv[u];
+        lv.dp[(size_t)l * sl + (size_t)(k0 + u) * sk] = dprev;
+      }
+    }
   }
   double xnext = 0.0;
   for (int k = len - 2; k >= 1; k--) {
     const size_t o = (size_t)l * sl + (size_t)k * sk;
-    const double x = fma(-lv.cp[o], xnext, lv.dp[o]);
+    const double x = fma(-cp_a[o], xnext, lv.dp[o]);
     xnext = x;
     const double D = (lv.GE[o] + lv.GE[o - 1]) + (lv.GN[o] + lv.GN[o - NX]);
     if (D > 0.0) { const double ec = lv.e[o]; lv.e[o] = ec + omega * (x - ec); }
@@ -261,13 +369,27 @@ static inline dim3 line_grid(int nline) {      // lines of one parity among 1 ..
 }
 
 // ---------------------------------------------------------------------------------------------
-cudaError_t launch_line_pass(const Layout& L, const Metrics& M, const uint8_t* celltype, const double* rhs, double* p,
-                             double* cpw, double* dpw, int dir, int parity, double omega, cudaStream_t st) {
-  return IFX_KLAUNCH(k_line_pass, line_grid(dir == 0 ? L.ny : L.nx), dim3(LINE_THREADS, 1, 1), st, L, M, celltype, rhs, p, cpw,
-                     dpw, dir, parity, omega);
+static inline dim3 all_lines_grid(int nline) { return dim3((nline - 2 + LINE_THREADS - 1) / LINE_THREADS, 1, 1); }
+
+cudaError_t launch_line_factor(const Layout& L, const Metrics& M, const uint8_t* celltype, int dir, double* inv_a, double* cp_a,
+                               cudaStream_t st) {
+  if (dir == 0) return IFX_KLAUNCH(k_line_factor<0>, all_lines_grid(L.ny), dim3(LINE_THREADS, 1, 1), st, L, M, celltype, inv_a, cp_a);
+  return IFX_KLAUNCH(k_line_factor<1>, all_lines_grid(L.nx), dim3(LINE_THREADS, 1, 1), st, L, M, celltype, inv_a, cp_a);
 }
-cudaError_t launch_mg_line_pass(MgLevel l, int dir, int parity, double omega, cudaStream_t st) {
-  return IFX_KLAUNCH(k_mg_line_pass, line_grid(dir == 0 ? l.ncy + 2 : l.ncx + 2), dim3(LINE_THREADS, 1, 1), st, l, dir, parity, omega);
+cudaError_t launch_line_solve(const Layout& L, const Metrics& M, const uint8_t* celltype, const double* rhs, double* p,
+                              const double* inv_a, const double* cp_a, double* dpw, int dir, int parity, double omega,
+                              cudaStream_t st) {
+  if (dir == 0)
+    return IFX_KLAUNCH(k_line_solve<0>, line_grid(L.ny), dim3(LINE_THREADS, 1, 1), st, L, M, celltype, rhs, p, inv_a, cp_a, dpw, parity, omega);
+  return IFX_KLAUNCH(k_line_solve<1>, line_grid(L.nx), dim3(LINE_THREADS, 1, 1), st, L, M, celltype, rhs, p, inv_a, cp_a, dpw, parity, omega);
+}
+cudaError_t launch_mg_line_factor(MgLevel l, int dir, cudaStream_t st) {
+  if (dir == 0) return IFX_KLAUNCH(k_mg_line_factor<0>, all_lines_grid(l.ncy + 2), dim3(LINE_THREADS, 1, 1), st, l);
+  return IFX_KLAUNCH(k_mg_line_factor<1>, all_lines_grid(l.ncx + 2), dim3(LINE_THREADS, 1, 1), st, l);
+}
+cudaError_t launch_mg_line_solve(MgLevel l, int dir, int parity, double omega, cudaStream_t st) {
+  if (dir == 0) return IFX_KLAUNCH(k_mg_line_solve<0>, line_grid(l.ncy + 2), dim3(LINE_THREADS, 1, 1), st, l, parity, omega);
+  return IFX_KLAUNCH(k_mg_line_solve<1>, line_grid(l.ncx + 2), dim3(LINE_THREADS, 1, 1), st, l, parity, omega);
 }
 cudaError_t launch_mg_build1(const Layout& L, const Metrics& M, const uint8_t* celltype, MgLevel c, int lines, cudaStream_t st) {
   return IFX_KLAUNCH(k_mg_build1, mg_grid(c.ncx, c.ncy), dim3(MG_BX, MG_BY, 1), st, L, M, celltype, c, lines);

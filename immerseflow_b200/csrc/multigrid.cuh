@@ -22,7 +22,8 @@ namespace ifx {
 struct MgLevel {
   int ncx, ncy;               // cells (without the ghost ring)
   double* GE; double* GN; double* e; double* R;
-  double* cp; double* dp;     // Thomas scratch of the line smoother (PPE_Solver 5 only, else null)
+  // line smoother (PPE_Solver 5 only, else null): stored elimination of the x-lines and of the y-lines, scratch
+  double* inv_x; double* cp_x; double* inv_y; double* cp_y; double* dp;
 };
 
 // levels for an ncx x ncy grid: halve while both counts are even and >= 4.  Returns the number of levels incl. level 0.
@@ -47,10 +48,15 @@ cudaError_t launch_mg_smooth(MgLevel l, int colour, double omega, cudaStream_t s
 cudaError_t launch_mg_restrict(MgLevel f, MgLevel c, cudaStream_t st);
 cudaError_t launch_mg_prolong(MgLevel c, MgLevel f, cudaStream_t st);
 cudaError_t launch_mg_prolong_fine(const Layout& L, const uint8_t* celltype, MgLevel c, double* p, cudaStream_t st);
-// zebra line relaxation (PPE_Solver 2; smoother of PPE_Solver 5): one pass over the lines of one parity, dir 0 = lines
-// along x (rows), dir 1 = along y (columns).  cpw / dpw: scratch fields in the layout of p.
-cudaError_t launch_line_pass(const Layout& L, const Metrics& M, const uint8_t* celltype, const double* rhs, double* p,
-                             double* cpw, double* dpw, int dir, int parity, double omega, cudaStream_t st);
-cudaError_t launch_mg_line_pass(MgLevel l, int dir, int parity, double omega, cudaStream_t st);
+// zebra line relaxation (PPE_Solver 2; smoother of PPE_Solver 5).  dir 0 = lines along x (rows), dir 1 = along y
+// (columns).  factor: elimination of the matrix of every line of one direction (depends on geometry and cell types
+// only) into inv_a / cp_a, fields in the layout of p; solve: one pass over the lines of one parity, dpw = scratch field.
+cudaError_t launch_line_factor(const Layout& L, const Metrics& M, const uint8_t* celltype, int dir, double* inv_a, double* cp_a,
+                               cudaStream_t st);
+cudaError_t launch_line_solve(const Layout& L, const Metrics& M, const uint8_t* celltype, const double* rhs, double* p,
+                              const double* inv_a, const double* cp_a, double* dpw, int dir, int parity, double omega,
+                              cudaStream_t st);
+cudaError_t launch_mg_line_factor(MgLevel l, int dir, cudaStream_t st);
+cudaError_t launch_mg_line_solve(MgLevel l, int dir, int parity, double omega, cudaStream_t st);
 
 }  // namespace ifx

@@ -88,7 +88,10 @@ struct ifx_solver {
   int mg_levels = 0;
   ifx::MgLevel mg[IFX_MG_MAX_LEVELS] = {};
   bool mg_valid = false;             // the conductances match the current cell types (cleared by ifx_iblank_update)
-  double *line_cp = nullptr, *line_dp = nullptr;   // fine-level Thomas scratch of the line relaxation (PPE_Solver 2, 5)
+  // fine level of the line relaxation (PPE_Solver 2, 5): stored elimination of the x-lines and of the y-lines
+  // (valid for the current cell types: cleared with mg_valid) and the solve's scratch; fields in the layout of p
+  double* line_f[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // inv_x, cp_x, inv_y, cp_y, dp
+  bool line_factor_valid = false;
 
   int kernel_variant = 4;            // 1: register-rolled direct loads (kernels_ad.cu / kernels_ppe.cu, reference mode only)
                                      // 4: bulk-copy row pipeline, lean interior path (kernels_v4.cu, default)

@@ -26,6 +26,9 @@ enum { cudaSuccess = 0 };
 
 extern thread_local dim3 threadIdx, blockIdx, blockDim, gridDim;
 
+inline int min(int a, int b) { return a < b ? a : b; }      // CUDA's global overloads
+inline int max(int a, int b) { return a > b ? a : b; }
+
 template <class F>
 inline void shim_launch(dim3 grid, dim3 block, F body) {
   gridDim = grid; blockDim = block;

@@ -16,8 +16,13 @@ static Metrics metrics_of(const double* const* t) {
   return M;
 }
 static Layout layout_of(int nx, int ny, int pitch) { return Layout{nx, ny, pitch, ny, 0, 1, ny - 1}; }
-static MgLevel level_of(int ncx, int ncy, double* GE, double* GN, double* e, double* R, double* cp = nullptr, double* dp = nullptr) {
-  return MgLevel{ncx, ncy, GE, GN, e, R, cp, dp};
+static MgLevel level_of(int ncx, int ncy, double* GE, double* GN, double* e, double* R, double* scratch5 = nullptr) {
+  MgLevel l{ncx, ncy, GE, GN, e, R, nullptr, nullptr, nullptr, nullptr, nullptr};
+  if (scratch5) {
+    const size_t n = (size_t)(ncx + 2) * (ncy + 2);
+    l.inv_x = scratch5; l.cp_x = scratch5 + n; l.inv_y = scratch5 + 2 * n; l.cp_y = scratch5 + 3 * n; l.dp = scratch5 + 4 * n;
+  }
+  return l;
 }
 
 void shim_mg_build1(int nx, int ny, int pitch, const double* const* tables, const uint8_t* ct, int ncx, int ncy, double* GE, double* GN, int lines) {
@@ -26,13 +31,17 @@ void shim_mg_build1(int nx, int ny, int pitch, const double* const* tables, cons
 void shim_mg_coarsen(int fx, int fy, double* fGE, double* fGN, int cx, int cy, double* GE, double* GN, int lines) {
   launch_mg_coarsen(level_of(fx, fy, fGE, fGN, nullptr, nullptr), level_of(cx, cy, GE, GN, nullptr, nullptr), lines, nullptr);
 }
+// one pass = factor of that direction (into scratch) + solve; the product factors once per set of cell types
 void shim_line_pass(int nx, int ny, int pitch, const double* const* tables, const uint8_t* ct, const double* rhs, double* p,
-                    double* cpw, double* dpw, int dir, int parity, double omega) {
-  launch_line_pass(layout_of(nx, ny, pitch), metrics_of(tables), ct, rhs, p, cpw, dpw, dir, parity, omega, nullptr);
+                    double* inv_a, double* cp_a, double* dpw, int dir, int parity, double omega) {
+  launch_line_factor(layout_of(nx, ny, pitch), metrics_of(tables), ct, dir, inv_a, cp_a, nullptr);
+  launch_line_solve(layout_of(nx, ny, pitch), metrics_of(tables), ct, rhs, p, inv_a, cp_a, dpw, dir, parity, omega, nullptr);
 }
-void shim_mg_line_pass(int ncx, int ncy, double* GE, double* GN, double* e, double* R, double* cp, double* dp, int dir, int parity,
+void shim_mg_line_pass(int ncx, int ncy, double* GE, double* GN, double* e, double* R, double* scratch5, int dir, int parity,
                        double omega) {
-  launch_mg_line_pass(level_of(ncx, ncy, GE, GN, e, R, cp, dp), dir, parity, omega, nullptr);
+  MgLevel l = level_of(ncx, ncy, GE, GN, e, R, scratch5);
+  launch_mg_line_factor(l, dir, nullptr);
+  launch_mg_line_solve(l, dir, parity, omega, nullptr);
 }
 void shim_mg_restrict_fine(int nx, int ny, int pitch, const double* const* tables, const uint8_t* ct, const double* rhs,
                            const double* p, int ncx, int ncy, double* R) {

@@ -139,10 +139,10 @@ def test_mg_kernels_match_oracle_bit_for_bit(shim, ncx, ncy, stretched, bodies, 
             L.orc_mg_smooth(NX, NY, P(GE[l]), P(GN[l]), P(R), colour, omega, P(e_o))
             shim.shim_mg_smooth(lx[l], ly[l], P(GE[l]), P(GN[l]), P(e_s), P(R), colour, omega)
             assert np.array_equal(e_o, e_s), f"smooth level {l} colour {colour}"
-        sc_o = [np.zeros(n), np.zeros(n)]; sc_s = [np.zeros(n), np.zeros(n)]
+        sc_o = [np.zeros(n), np.zeros(n)]; sc_s = np.zeros(5 * n)
         for d, par in ((0, 0), (0, 1), (1, 0), (1, 1), (0, 0)):      # zebra line relaxation
             L.orc_mg_line_pass(NX, NY, P(GE[l]), P(GN[l]), P(R), d, par, omega, P(e_o), P(sc_o[0]), P(sc_o[1]))
-            shim.shim_mg_line_pass(lx[l], ly[l], P(GE[l]), P(GN[l]), P(e_s), P(R), P(sc_s[0]), P(sc_s[1]), d, par, omega)
+            shim.shim_mg_line_pass(lx[l], ly[l], P(GE[l]), P(GN[l]), P(e_s), P(R), P(sc_s), d, par, omega)
             assert np.array_equal(e_o, e_s), f"line pass level {l} dir {d} parity {par}"
         if l + 1 < nlev:
             nc = (lx[l + 1] + 2) * (ly[l + 1] + 2)
@@ -157,10 +157,10 @@ def test_mg_kernels_match_oracle_bit_for_bit(shim, ncx, ncy, stretched, bodies, 
 
     # ---- zebra line relaxation on the fine level (in place; scratch in the layout of p)
     p_o = p.copy(); pp2 = pad(p, nx, ny)
-    so = [np.zeros(N), np.zeros(N)]; ss = [np.zeros(pp2.size), np.zeros(pp2.size)]
+    so = [np.zeros(N), np.zeros(N)]; ss = [np.zeros(pp2.size), np.zeros(pp2.size), np.zeros(pp2.size)]
     for d, par in ((0, 0), (0, 1), (1, 0), (1, 1), (1, 0), (0, 1)):
         L.orc_ppe_line_pass(nx, ny, P(cP), P(cxm), P(cxp), P(cym), P(cyp), u8(ct), P(rhs), d, par, omega, P(p_o), P(so[0]), P(so[1]))
-        shim.shim_line_pass(nx, ny, pitch, tarr, u8(ctp), P(rp), P(pp2), P(ss[0]), P(ss[1]), d, par, omega)
+        shim.shim_line_pass(nx, ny, pitch, tarr, u8(ctp), P(rp), P(pp2), P(ss[0]), P(ss[1]), P(ss[2]), d, par, omega)
         assert np.array_equal(unpad(pp2, nx, ny), p_o), f"fine line pass dir {d} parity {par}"
     assert not np.array_equal(p_o, p)
     if bodies:      # a line solve is exact along the line: the residual of the rows just relaxed with omega = 1 vanishes there
