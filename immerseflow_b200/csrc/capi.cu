@@ -1018,7 +1018,7 @@ static int mg_coarse_cycle(ifx_solver* s) {
   }
   for (int l = Lv - 2; l >= 1; l--) {
     s->launches++;
-    IFX_CUDA(s, launch_mg_prolong(s->mg[l + 1], s->mg[l], s->stream));
+    IFX_CUDA(s, launch_mg_prolong(s->mg[l + 1], s->mg[l], 0, s->stream));
     if ((rc = smooth(l, IFX_MG_NU2)) != IFX_OK) return rc;
   }
   return IFX_OK;
@@ -1094,7 +1094,7 @@ int ifx::run_ppe_multigrid(ifx_solver* s, ifx_step_stats* st) {
       IFX_CUDA(s, launch_mg_restrict_fine(L, s->M, s->celltype, s->rhs, s->p[base], s->mg[1], s->stream));
       if ((rc = mg_coarse_cycle(s)) != IFX_OK) return rc;
       s->launches++;
-      IFX_CUDA(s, launch_mg_prolong_fine(L, s->celltype, s->mg[1], s->p[base], s->stream));
+      IFX_CUDA(s, launch_mg_prolong_fine(L, s->celltype, s->mg[1], s->p[base], 0, s->stream));
       for (int k = 0; k < IFX_MG_NU2; k++) {
         if ((rc = red(0, 0, 0, false)) != IFX_OK) return rc;
         if ((rc = black()) != IFX_OK) return rc;
@@ -1225,11 +1225,11 @@ int ifx::run_ppe_lines(ifx_solver* s, ifx_step_stats* st) {
       }
       for (int l = Lv - 2; l >= 1; l--) {
         s->launches++;
-        IFX_CUDA(s, launch_mg_prolong(s->mg[l + 1], s->mg[l], s->stream));
+        IFX_CUDA(s, launch_mg_prolong(s->mg[l + 1], s->mg[l], 1, s->stream));
         if ((rc = coarse_lines(l, IFX_MG_NU2)) != IFX_OK) return rc;
       }
       s->launches++;
-      IFX_CUDA(s, launch_mg_prolong_fine(L, s->celltype, s->mg[1], s->p[base], s->stream));
+      IFX_CUDA(s, launch_mg_prolong_fine(L, s->celltype, s->mg[1], s->p[base], 1, s->stream));
       if ((rc = fine_lines(IFX_MG_NU2)) != IFX_OK) return rc;
     }
     K = s->h_ctl->iter;

@@ -139,26 +139,43 @@ static __global__ void k_mg_restrict(MgLevel f, MgLevel c) {
   c.R[cidx(I, J, c.ncx + 2)] = (r[0] + r[1]) + (r[2] + r[3]);
 }
 
-// e_l += e_{l+1}(parent) on the active cells of level l (oracle: orc_mg_prolong)
-static __global__ void k_mg_prolong(MgLevel c, MgLevel f) {
+// Bilinear prolongation of the line-smoothed cycle (oracle: prolong_value): parent 9/16, the two nearer coarse neighbours
+// 3/16 each, the diagonal one 1/16; a neighbour not connected to the parent through open coarse faces counts as the parent.
+__device__ __forceinline__ double mg_prolong_value(int i, int j, const MgLevel& c, int bilinear) {
+  const int NX = c.ncx + 2;
+  const int I = (i + 1) / 2, J = (j + 1) / 2;
+  const size_t P = cidx(I, J, NX);
+  const double eP = c.e[P];
+  if (!bilinear) return eP;
+  const int di = (i & 1) ? -1 : 1, dj = (j & 1) ? -1 : 1;
+  const size_t A = P + di, B = P + (ptrdiff_t)dj * NX, C = A + (ptrdiff_t)dj * NX;
+  const double gPA = c.GE[di > 0 ? P : A], gPB = c.GN[dj > 0 ? P : B];
+  const double gAC = c.GN[dj > 0 ? A : C], gBC = c.GE[di > 0 ? B : C];
+  const double eA = (gPA > 0.0) ? c.e[A] : eP;
+  const double eB = (gPB > 0.0) ? c.e[B] : eP;
+  const double eC = ((gPA > 0.0 && gAC > 0.0) || (gPB > 0.0 && gBC > 0.0)) ? c.e[C] : eP;
+  return 0.0625 * ((9.0 * eP + 3.0 * eA) + (3.0 * eB + eC));
+}
+
+// e_l += P e_{l+1} on the active cells of level l (oracle: orc_mg_prolong / orc_mg_prolong2)
+static __global__ void k_mg_prolong(MgLevel c, MgLevel f, int bilinear) {
   const int i = 1 + blockIdx.x * blockDim.x + threadIdx.x, j = 1 + blockIdx.y * blockDim.y + threadIdx.y;
   if (i > f.ncx || j > f.ncy) return;
   const int nxl = f.ncx + 2;
   const size_t o = cidx(i, j, nxl);
   const double D = (f.GE[o] + f.GE[o - 1]) + (f.GN[o] + f.GN[o - nxl]);
   if (!(D > 0.0)) return;
-  f.e[o] = f.e[o] + c.e[cidx((i + 1) / 2, (j + 1) / 2, c.ncx + 2)];
+  f.e[o] = f.e[o] + mg_prolong_value(i, j, c, bilinear);
 }
 
-// p += e_1(parent) on fluid cells (oracle: orc_mg_prolong_fine)
-static __global__ void k_mg_prolong_fine(Layout L, const uint8_t* __restrict__ ct, MgLevel c, double* __restrict__ p) {
+// p += P e_1 on fluid cells (oracle: orc_mg_prolong_fine / orc_mg_prolong_fine2)
+static __global__ void k_mg_prolong_fine(Layout L, const uint8_t* __restrict__ ct, MgLevel c, double* __restrict__ p, int bilinear) {
   const int i = 1 + blockIdx.x * blockDim.x + threadIdx.x, j = 1 + blockIdx.y * blockDim.y + threadIdx.y;
   if (i > L.nx - 2 || j > L.ny - 2) return;
   const size_t o = lidx(L, i, j - L.j0);
   if (ct[o] != IFX_FLUID) return;
-  p[o] = p[o] + c.e[cidx((i + 1) / 2, (j + 1) / 2, c.ncx + 2)];
+  p[o] = p[o] + mg_prolong_value(i, j, c, bilinear);
 }
-
 
 // ---------------------------------------------------------------------------------------------
 // Zebra line relaxation (oracle: orc_ppe_line_pass / orc_mg_line_pass).  One thread per line, Thomas elimination in
@@ -407,11 +424,11 @@ cudaError_t launch_mg_smooth(MgLevel l, int colour, double omega, cudaStream_t s
 cudaError_t launch_mg_restrict(MgLevel f, MgLevel c, cudaStream_t st) {
   return IFX_KLAUNCH(k_mg_restrict, mg_grid(c.ncx, c.ncy), dim3(MG_BX, MG_BY, 1), st, f, c);
 }
-cudaError_t launch_mg_prolong(MgLevel c, MgLevel f, cudaStream_t st) {
-  return IFX_KLAUNCH(k_mg_prolong, mg_grid(f.ncx, f.ncy), dim3(MG_BX, MG_BY, 1), st, c, f);
+cudaError_t launch_mg_prolong(MgLevel c, MgLevel f, int bilinear, cudaStream_t st) {
+  return IFX_KLAUNCH(k_mg_prolong, mg_grid(f.ncx, f.ncy), dim3(MG_BX, MG_BY, 1), st, c, f, bilinear);
 }
-cudaError_t launch_mg_prolong_fine(const Layout& L, const uint8_t* celltype, MgLevel c, double* p, cudaStream_t st) {
-  return IFX_KLAUNCH(k_mg_prolong_fine, mg_grid(L.nx - 2, L.ny - 2), dim3(MG_BX, MG_BY, 1), st, L, celltype, c, p);
+cudaError_t launch_mg_prolong_fine(const Layout& L, const uint8_t* celltype, MgLevel c, double* p, int bilinear, cudaStream_t st) {
+  return IFX_KLAUNCH(k_mg_prolong_fine, mg_grid(L.nx - 2, L.ny - 2), dim3(MG_BX, MG_BY, 1), st, L, celltype, c, p, bilinear);
 }
 
 }  // namespace ifx

@@ -46,8 +46,9 @@ cudaError_t launch_mg_restrict_fine(const Layout& L, const Metrics& M, const uin
                                     const double* p, MgLevel c, cudaStream_t st);
 cudaError_t launch_mg_smooth(MgLevel l, int colour, double omega, cudaStream_t st);
 cudaError_t launch_mg_restrict(MgLevel f, MgLevel c, cudaStream_t st);
-cudaError_t launch_mg_prolong(MgLevel c, MgLevel f, cudaStream_t st);
-cudaError_t launch_mg_prolong_fine(const Layout& L, const uint8_t* celltype, MgLevel c, double* p, cudaStream_t st);
+// bilinear = 0: piecewise-constant prolongation (point-smoothed cycle); 1: bilinear, coarse conductances as connectivity
+cudaError_t launch_mg_prolong(MgLevel c, MgLevel f, int bilinear, cudaStream_t st);
+cudaError_t launch_mg_prolong_fine(const Layout& L, const uint8_t* celltype, MgLevel c, double* p, int bilinear, cudaStream_t st);
 // zebra line relaxation (PPE_Solver 2; smoother of PPE_Solver 5).  dir 0 = lines along x (rows), dir 1 = along y
 // (columns).  factor: elimination of the matrix of every line of one direction (depends on geometry and cell types
 // only) into inv_a / cp_a, fields in the layout of p; solve: one pass over the lines of one parity, dpw = scratch field.

@@ -189,6 +189,11 @@ void orc_mg_restrict(int nxl, const double* GE, const double* GN, const double* 
                      double* Rc);
 void orc_mg_prolong(int nxl, int nyl, const double* GE, const double* GN, int NX, const double* ec, double* e);
 void orc_mg_prolong_fine(int nx, int ny, const unsigned char* ct, int NX, const double* e1, double* p);
+/* GEc / GNc != NULL: bilinear prolongation with the coarse level's conductances as the connectivity (PPE_Solver 5) */
+void orc_mg_prolong2(int nxl, int nyl, const double* GE, const double* GN, int NX, const double* ec, const double* GEc,
+                     const double* GNc, double* e);
+void orc_mg_prolong_fine2(int nx, int ny, const unsigned char* ct, int NX, const double* e1, const double* GE1,
+                          const double* GN1, double* p);
 void orc_mg_coarse_cycle(orc_mg* m, int nu1, int nu2, int ncoarse, double omega);
 void orc_mg_vcycle(orc_mg* m, int nx, int ny, const double* dx, const double* dy, const double* cP, const double* cxm,
                    const double* cxp, const double* cym, const double* cyp, const unsigned char* ct, const double* rhs,

@@ -50,6 +50,10 @@ struct orc_mg {
   double *cpw[ORC_MG_MAX_LEVELS], *dpw[ORC_MG_MAX_LEVELS];      /* Thomas scratch of the line smoother */
 };
 orc_mg* orc_mg_create2(int nx, int ny, const double* dx, const double* dy, const unsigned char* celltype, int lines);
+void orc_mg_prolong2(int nxl, int nyl, const double* GE, const double* GN, int NX, const double* ec, const double* GEc,
+                     const double* GNc, double* e);
+void orc_mg_prolong_fine2(int nx, int ny, const unsigned char* ct, int NX, const double* e1, const double* GE1,
+                          const double* GN1, double* p);
 
 int orc_mg_plan(int ncx, int ncy, int* lx, int* ly) {
   int n = 1;
@@ -225,25 +229,52 @@ void orc_mg_restrict(int nxl, const double* GE, const double* GN, const double* 
     }
 }
 
-/* e_l += e_{l+1}(parent) on active cells of level l */
+/* Bilinear prolongation (the line-smoothed cycle; the point-smoothed one converges faster with the piecewise-constant
+ * transfer, 0.13 against 0.18 per cycle, the line-smoothed one with this, 0.17 against 0.36).  Value of the coarse
+ * correction at fine cell (i, j): parent 9/16, the two nearer coarse neighbours 3/16 each, the diagonal one 1/16; a
+ * neighbour that is not connected to the parent through open coarse faces (inactive cell, body in between, grid
+ * boundary) is replaced by the parent. */
+static double prolong_value(int i, int j, int NX, const double* ec, const double* GEc, const double* GNc) {
+  const int I = (i + 1) / 2, J = (j + 1) / 2;
+  const int di = (i & 1) ? -1 : 1, dj = (j & 1) ? -1 : 1;
+  const int P = ID(I, J, NX), A = P + di, B = P + dj * NX, C = A + dj * NX;
+  const double eP = ec[P];
+  /* conductance of the face between two horizontally / vertically adjacent coarse cells */
+  const double gPA = GEc[di > 0 ? P : A], gPB = GNc[dj > 0 ? P : B];
+  const double gAC = GNc[dj > 0 ? A : C], gBC = GEc[di > 0 ? B : C];
+  const double eA = (gPA > 0.0) ? ec[A] : eP;
+  const double eB = (gPB > 0.0) ? ec[B] : eP;
+  const double eC = ((gPA > 0.0 && gAC > 0.0) || (gPB > 0.0 && gBC > 0.0)) ? ec[C] : eP;
+  return 0.0625 * ((9.0 * eP + 3.0 * eA) + (3.0 * eB + eC));
+}
+
+/* e_l += e_{l+1}(parent) on active cells of level l; prolong2 with GEc != NULL: bilinear (see prolong_value) */
 void orc_mg_prolong(int nxl, int nyl, const double* GE, const double* GN, int NX, const double* ec, double* e) {
+  orc_mg_prolong2(nxl, nyl, GE, GN, NX, ec, NULL, NULL, e);
+}
+void orc_mg_prolong2(int nxl, int nyl, const double* GE, const double* GN, int NX, const double* ec, const double* GEc,
+                     const double* GNc, double* e) {
 #pragma omp parallel for
   for (int j = 1; j < nyl - 1; j++)
     for (int i = 1; i < nxl - 1; i++) {
       const int id = ID(i, j, nxl);
       const double D = (GE[id] + GE[id - 1]) + (GN[id] + GN[id - nxl]);
       if (!(D > 0.0)) continue;
-      e[id] = e[id] + ec[ID((i + 1) / 2, (j + 1) / 2, NX)];
+      e[id] = e[id] + (GEc ? prolong_value(i, j, NX, ec, GEc, GNc) : ec[ID((i + 1) / 2, (j + 1) / 2, NX)]);
     }
 }
 
 /* p += e_1(parent) on fluid cells */
 void orc_mg_prolong_fine(int nx, int ny, const unsigned char* ct, int NX, const double* e1, double* p) {
+  orc_mg_prolong_fine2(nx, ny, ct, NX, e1, NULL, NULL, p);
+}
+void orc_mg_prolong_fine2(int nx, int ny, const unsigned char* ct, int NX, const double* e1, const double* GE1,
+                          const double* GN1, double* p) {
 #pragma omp parallel for
   for (int j = 1; j < ny - 1; j++)
     for (int i = 1; i < nx - 1; i++) {
       const int id = ID(i, j, nx);
-      if (IS_FLUID(ct[id])) p[id] = p[id] + e1[ID((i + 1) / 2, (j + 1) / 2, NX)];
+      if (IS_FLUID(ct[id])) p[id] = p[id] + (GE1 ? prolong_value(i, j, NX, e1, GE1, GN1) : e1[ID((i + 1) / 2, (j + 1) / 2, NX)]);
     }
 }
 
@@ -427,9 +458,10 @@ void orc_mg_vcycle_lines(orc_mg* m, int nx, int ny, const double* dx, const doub
       orc_mg_restrict(NX, m->GE[l], m->GN[l], m->R[l], m->e[l], m->ncx[l + 1] + 2, m->ncy[l + 1] + 2, m->R[l + 1]);
   }
   for (int l = L - 2; l >= 1; l--) {
-    orc_mg_prolong(m->ncx[l] + 2, m->ncy[l] + 2, m->GE[l], m->GN[l], m->ncx[l + 1] + 2, m->e[l + 1], m->e[l]);
+    orc_mg_prolong2(m->ncx[l] + 2, m->ncy[l] + 2, m->GE[l], m->GN[l], m->ncx[l + 1] + 2, m->e[l + 1], m->GE[l + 1],
+                    m->GN[l + 1], m->e[l]);
     mg_lines(m, l, nu2, omega);
   }
-  orc_mg_prolong_fine(nx, ny, ct, m->ncx[1] + 2, m->e[1], p);
+  orc_mg_prolong_fine2(nx, ny, ct, m->ncx[1] + 2, m->e[1], m->GE[1], m->GN[1], p);
   for (int k = 0; k < nu2; k++) orc_ppe_line_iteration(nx, ny, cP, cxm, cxp, cym, cyp, ct, rhs, omega, p, cpw, dpw);
 }

@@ -53,10 +53,11 @@ void shim_mg_smooth(int ncx, int ncy, double* GE, double* GN, double* e, double*
 void shim_mg_restrict(int fx, int fy, double* GE, double* GN, double* e, double* R, int cx, int cy, double* Rc) {
   launch_mg_restrict(level_of(fx, fy, GE, GN, e, R), level_of(cx, cy, nullptr, nullptr, nullptr, Rc), nullptr);
 }
-void shim_mg_prolong(int cx, int cy, double* ec, int fx, int fy, double* GE, double* GN, double* e) {
-  launch_mg_prolong(level_of(cx, cy, nullptr, nullptr, ec, nullptr), level_of(fx, fy, GE, GN, e, nullptr), nullptr);
+void shim_mg_prolong(int cx, int cy, double* cGE, double* cGN, double* ec, int fx, int fy, double* GE, double* GN, double* e, int bilinear) {
+  launch_mg_prolong(level_of(cx, cy, cGE, cGN, ec, nullptr), level_of(fx, fy, GE, GN, e, nullptr), bilinear, nullptr);
 }
-void shim_mg_prolong_fine(int nx, int ny, int pitch, const uint8_t* ct, int cx, int cy, double* e1, double* p) {
-  launch_mg_prolong_fine(layout_of(nx, ny, pitch), ct, level_of(cx, cy, nullptr, nullptr, e1, nullptr), p, nullptr);
+void shim_mg_prolong_fine(int nx, int ny, int pitch, const uint8_t* ct, int cx, int cy, double* cGE, double* cGN, double* e1, double* p,
+                          int bilinear) {
+  launch_mg_prolong_fine(layout_of(nx, ny, pitch), ct, level_of(cx, cy, cGE, cGN, e1, nullptr), p, bilinear, nullptr);
 }
 }

@@ -152,8 +152,12 @@ def test_mg_kernels_match_oracle_bit_for_bit(shim, ncx, ncy, stretched, bodies, 
             assert np.array_equal(Rc_o, Rc_s), f"restrict level {l}"
             ec = rng.standard_normal(nc)
             L.orc_mg_prolong(NX, NY, P(GE[l]), P(GN[l]), lx[l + 1] + 2, P(ec), P(e_o))
-            shim.shim_mg_prolong(lx[l + 1], ly[l + 1], P(ec), lx[l], ly[l], P(GE[l]), P(GN[l]), P(e_s))
+            shim.shim_mg_prolong(lx[l + 1], ly[l + 1], None, None, P(ec), lx[l], ly[l], P(GE[l]), P(GN[l]), P(e_s), 0)
             assert np.array_equal(e_o, e_s), f"prolong level {l}"
+            GEc, GNc = olevel(l + 1, 0), olevel(l + 1, 1)           # bilinear, coarse conductances as connectivity
+            L.orc_mg_prolong2(NX, NY, P(GE[l]), P(GN[l]), lx[l + 1] + 2, P(ec), P(GEc), P(GNc), P(e_o))
+            shim.shim_mg_prolong(lx[l + 1], ly[l + 1], P(GEc), P(GNc), P(ec), lx[l], ly[l], P(GE[l]), P(GN[l]), P(e_s), 1)
+            assert np.array_equal(e_o, e_s), f"bilinear prolong level {l}"
 
     # ---- zebra line relaxation on the fine level (in place; scratch in the layout of p)
     p_o = p.copy(); pp2 = pad(p, nx, ny)
@@ -175,7 +179,14 @@ def test_mg_kernels_match_oracle_bit_for_bit(shim, ncx, ncy, stretched, bodies, 
     e1 = rng.standard_normal(n1)
     p_o = p.copy()
     L.orc_mg_prolong_fine(nx, ny, u8(ct), lx[1] + 2, P(e1), P(p_o))
-    shim.shim_mg_prolong_fine(nx, ny, pitch, u8(ctp), lx[1], ly[1], P(e1), P(pp))
+    shim.shim_mg_prolong_fine(nx, ny, pitch, u8(ctp), lx[1], ly[1], None, None, P(e1), P(pp), 0)
     assert np.array_equal(unpad(pp, nx, ny), p_o)
     assert not np.array_equal(p_o, p)
+    L.orc_mg_prolong_fine2(nx, ny, u8(ct), lx[1] + 2, P(e1), P(GE[1]), P(GN[1]), P(p_o))
+    shim.shim_mg_prolong_fine(nx, ny, pitch, u8(ctp), lx[1], ly[1], P(GE[1]), P(GN[1]), P(e1), P(pp), 1)
+    assert np.array_equal(unpad(pp, nx, ny), p_o)
+    # a constant coarse correction is reproduced exactly by both transfers, bodies or not
+    one = np.ones(n1); q_o = np.zeros(N)
+    L.orc_mg_prolong_fine2(nx, ny, u8(ct), lx[1] + 2, P(one), P(GE[1]), P(GN[1]), P(q_o))
+    assert set(np.unique(q_o)) <= {0.0, 1.0} and q_o.sum() == (ct.reshape(ny, nx)[1:-1, 1:-1] == 1).sum()
     L.orc_mg_destroy(mg)

@@ -98,7 +98,7 @@ def stretched_case(ncx, ncy, solver, omega, itermax, tol=1e-30):
 
 def test_line_smoothed_multigrid_converges_on_stretched_grids():
     """PPE_Solver 5: where the point-smoothed cycle crawls (cell aspect ratios of 10+), alternating zebra line relaxation
-    as the smoother gives a grid-independent 0.3-0.4 per V(2,2) cycle; PPE_Solver 2 (line SOR alone) and 3 (point SOR)
+    as the smoother (with bilinear prolongation) gives 0.13-0.18 per V(2,2) cycle from 128 x 64 to 512 x 256; PPE_Solver 2 (line SOR alone) and 3 (point SOR)
     are single-grid methods and barely move in the same number of iterations."""
     rates = {}
     for n in ((128, 64), (256, 128), (512, 256)):
@@ -107,7 +107,7 @@ def test_line_smoothed_multigrid_converges_on_stretched_grids():
             s, _ = stretched_case(n[0], n[1], 5, 1.0, k)
             r.append(s.poisson()[4]); s.close()
         rates[n] = (r[1] / r[0]) ** (1.0 / 8.0)
-    assert max(rates.values()) < 0.45, rates
+    assert max(rates.values()) < 0.25, rates
     s, _ = stretched_case(256, 128, 4, 1.0, 10); r4 = s.poisson()[4]; s.close()
     s, _ = stretched_case(256, 128, 5, 1.0, 10); r5 = s.poisson()[4]; s.close()
     s, _ = stretched_case(256, 128, 2, 1.0, 10); r2 = s.poisson()[4]; s.close()
