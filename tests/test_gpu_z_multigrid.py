@@ -1,6 +1,7 @@
 """PPE_Solver 4 — geometric multigrid on the GPU through the C-ABI, against oracle/ifx_oracle_mg.c:
 pressure bit-exact after every step, identical V-cycle counts.  PARITY UNPINNED (the reference has no multigrid);
-tests/test_mg_shim.py runs the same kernel source on the CPU."""
+tests/test_mg_shim.py runs the same kernel source on the CPU.  (The file name sorts after the pinned-parity suites on
+purpose: `pytest -x` reaches the reference-parity and slab tests first.)"""
 import numpy as np
 import pytest
 
