@@ -196,6 +196,16 @@ static __global__ void k_mg_prolong_fine(Layout L, const uint8_t* __restrict__ c
 // ---------------------------------------------------------------------------------------------
 constexpr int LINE_THREADS = 32;
 constexpr int LINE_U = 8;
+constexpr int LINE_AHEAD = 4 * LINE_U;      // cells ahead of the chain whose cache lines are requested early
+
+// a hint, not a load: the line is on its way into L1/L2 when the loads of LINE_AHEAD cells later ask for it
+__device__ __forceinline__ void line_prefetch(const void* a) {
+#ifndef IFX_HOST_SHIM
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(a));
+#else
+  (void)a;
+#endif
+}
 
 template <int DIR>
 static __global__ void k_line_factor(Layout L, Metrics M, const uint8_t* __restrict__ ct, double* __restrict__ inv_a,
@@ -251,6 +261,13 @@ static __global__ void k_line_solve(Layout L, Metrics M, const uint8_t* __restri
     const int n = min(LINE_U, len - 1 - k0);
     double v_inv[LINE_U], v_rhs[LINE_U], v_phi[LINE_U], v_plo[LINE_U], v_pc[LINE_U], v_ca[LINE_U];
     uint8_t v_ct[LINE_U], v_chi[LINE_U], v_clo[LINE_U];
+    if (k0 + LINE_AHEAD + LINE_U <= len - 1) {             // one thread owns the whole line: too few threads to hide DRAM latency
+#pragma unroll
+      for (int u = 0; u < LINE_U; u += (DIR == 0 ? 4 : 1)) {   // x-lines: 4 doubles per 32-byte sector; y-lines: a line per cell
+        const size_t o = o0 + (size_t)(k0 + LINE_AHEAD + u) * sk;
+        line_prefetch(inv_a + o); line_prefetch(rhs + o); line_prefetch(p + o); line_prefetch(p + o + sc); line_prefetch(p + o - sc);
+      }
+    }
 #pragma unroll
     for (int u = 0; u < LINE_U; u++) {
       if (u < n) {
@@ -285,6 +302,13 @@ static __global__ void k_line_solve(Layout L, Metrics M, const uint8_t* __restri
     const int n = min(LINE_U, k1);
     double v_cp[LINE_U], v_dp[LINE_U], v_pc[LINE_U];
     uint8_t v_ct[LINE_U];
+    if (k1 - LINE_AHEAD - LINE_U >= 0) {
+#pragma unroll
+      for (int u = 0; u < LINE_U; u += (DIR == 0 ? 4 : 1)) {
+        const size_t o = o0 + (size_t)(k1 - LINE_AHEAD - u) * sk;
+        line_prefetch(cp_a + o); line_prefetch(dpw + o); line_prefetch(p + o);
+      }
+    }
 #pragma unroll
     for (int u = 0; u < LINE_U; u++) {
       if (u < n) {
