@@ -419,6 +419,23 @@ def main():
             s.get(k, host_in[k])
         nh = max(1, min(args.e2e_handles, 3))
         reps = max(1, args.steps)
+        sims, host_out, fallback = [], None, None
+        if nh > 1:
+            # handles whose control traffic does not queue behind the bulk transfers (ifx_options.zero_copy_control).
+            # If the box cannot hold them (device memory, page-locked host memory), every rank falls back to one handle.
+            try:
+                sims = [make_solver(1) for _ in range(nh)]
+                host_out = [{k: torch.empty(n, dtype=torch.float64, pin_memory=True).numpy() for k in names} for _ in range(2)]
+            except Exception as ex:       # noqa: BLE001 — reported in the JSON line
+                fallback = f"{type(ex).__name__}: {ex}"[:200]
+            ok = torch.tensor([0.0 if fallback else 1.0], device="cuda")
+            if world > 1:
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if ok.item() < 1.0:
+                fallback = fallback or "another rank could not set up its handles"
+                for h in sims:
+                    h.close()
+                sims, host_out, nh = [], None, 1
         if nh == 1:
             barrier()
             t0 = time.perf_counter()
@@ -430,9 +447,6 @@ def main():
                     s.get(k, host_in[k])
             barrier()
         else:
-            # handles whose control traffic does not queue behind the bulk transfers (ifx_options.zero_copy_control)
-            sims = [make_solver(1) for _ in range(nh)]
-            host_out = [{k: torch.empty(n, dtype=torch.float64, pin_memory=True).numpy() for k in names} for _ in range(2)]
             for h in sims:                         # every handle allocates its lazily sized buffers before the clock starts
                 one_step(h)
             barrier()
@@ -464,7 +478,7 @@ def main():
         e2e = {"value": cells / te / 1e6, "unit": METRIC, "h2d_bytes_per_step": 3 * 8 * n, "d2h_bytes_per_step": 3 * 8 * n,
                "ms_per_step": te * 1e3, "steps": reps,
                "pipeline": (f"{nh} simulations in flight (upload | step | download overlapped), fill + drain timed" if nh > 1
-                            else "upload, step, download in series")}
+                            else "upload, step, download in series" + (f" (fallback: {fallback})" if fallback else ""))}
         if nh > 1:
             if world > 1:
                 dist.barrier()                     # nobody frees a segment a neighbour may still be storing into
