@@ -339,7 +339,7 @@ extern "C" int ifx_create(const ifx_input* in, const double* xf, const double* y
   if (opt.ppe_solver == 4 || opt.ppe_solver == 5) {
     int lx[IFX_MG_MAX_LEVELS], ly[IFX_MG_MAX_LEVELS];
     if (mg_plan(in->nx - 2, in->ny - 2, lx, ly) < 2)
-      return fail(nullptr, IFX_ERR_INVALID, "multigrid needs even cell counts (>= 4) in both directions");
+      return fail(nullptr, IFX_ERR_INVALID, "multigrid needs at least 3 cells in both directions");
   }
   if ((opt.ppe_solver == 2 || opt.ppe_solver >= 4) && opt.nranks > 1)
     return fail(nullptr, IFX_ERR_INVALID, "line SOR and multigrid are single-GPU for now (slab runs: ppe_solver 1 or 3)");
@@ -960,7 +960,7 @@ static int mg_ensure(ifx_solver* s) {
   if (s->mg_levels == 0) {
     int lx[IFX_MG_MAX_LEVELS], ly[IFX_MG_MAX_LEVELS];
     const int n = mg_plan(s->L.nx - 2, s->L.ny - 2, lx, ly);
-    if (n < 2) return fail(s, IFX_ERR_INVALID, "multigrid needs even cell counts (>= 4) in both directions");
+    if (n < 2) return fail(s, IFX_ERR_INVALID, "multigrid needs at least 3 cells in both directions");
     for (int l = 1; l < n; l++) {
       const size_t bytes = sizeof(double) * (size_t)(lx[l] + 2) * (ly[l] + 2);
       s->mg[l].ncx = lx[l]; s->mg[l].ncy = ly[l];

@@ -42,10 +42,12 @@ static __global__ void k_mg_build1(Layout L, Metrics M, const uint8_t* __restric
   double ge[2] = {0.0, 0.0}, gn[2] = {0.0, 0.0};
 #pragma unroll
   for (int k = 0; k < 2; k++) {
-    const int jj = j - 1 + k, ii = i - 1 + k;
+    const int jj = j - 1 + k, ii = i - 1 + k;       // the second child row / column may not exist (odd count)
     const size_t oe = lidx(L, i, jj - L.j0), on = lidx(L, ii, j - L.j0);
-    if (i <= L.nx - 3 && ct[oe] == IFX_FLUID && ct[oe + 1] == IFX_FLUID) ge[k] = (2.0 * M.dy[jj]) / (M.dx[i] + M.dx[i + 1]);
-    if (j <= L.ny - 3 && ct[on] == IFX_FLUID && ct[on + L.pitch] == IFX_FLUID) gn[k] = (2.0 * M.dx[ii]) / (M.dy[j] + M.dy[j + 1]);
+    if (i <= L.nx - 3 && jj <= L.ny - 2 && ct[oe] == IFX_FLUID && ct[oe + 1] == IFX_FLUID)
+      ge[k] = (2.0 * M.dy[jj]) / (M.dx[i] + M.dx[i + 1]);
+    if (j <= L.ny - 3 && ii <= L.nx - 2 && ct[on] == IFX_FLUID && ct[on + L.pitch] == IFX_FLUID)
+      gn[k] = (2.0 * M.dx[ii]) / (M.dy[j] + M.dy[j + 1]);
   }
   const double sx = ge[0] + ge[1], sy = gn[0] + gn[1];
   double ax, ay;
@@ -83,7 +85,7 @@ static __global__ void k_mg_restrict_fine(Layout L, Metrics M, const uint8_t* __
     const int i = 2 * I - 1 + (k & 1), j = 2 * J - 1 + (k >> 1);
     const size_t o = lidx(L, i, j - L.j0);
     r[k] = 0.0;
-    if (ct[o] != IFX_FLUID) continue;
+    if (i > L.nx - 2 || j > L.ny - 2 || ct[o] != IFX_FLUID) continue;      // child beyond the grid (odd count)
     const double pc = p[o];
     const double pw = (i == 1 || ct[o - 1] != IFX_FLUID) ? pc : p[o - 1];
     const double pe = (i == L.nx - 2 || ct[o + 1] != IFX_FLUID) ? pc : p[o + 1];

@@ -78,7 +78,7 @@ static void usage() {
       "  --ppe-solver 3 (or PPE_Solver 3 in inputs.txt; full mode): red-black SOR with factor --ppe-omega / w-PPE.\n"
       "  --ppe-solver 2 (PPE_Solver 2, the input file's \"Line SOR\"): zebra line relaxation, factor --ppe-omega / w-PPE.\n"
       "  --ppe-solver 4 / 5: geometric multigrid V(2,2) cycles smoothed by red-black SOR (uniform grids) / by line\n"
-      "  relaxation (stretched grids); even cell counts; PPE_itermax then counts cycles.\n"
+      "  relaxation (stretched grids); PPE_itermax then counts cycles.\n"
       "  --bodies FILE (full mode): `nbodies`, then per body a line `nmarkers ub vb [ax ay f]` and nmarkers lines `x y`\n"
       "  (counter-clockwise).  A body translates as x0 + ub t + ax sin(2 pi f t) (same in y); moving bodies are\n"
       "  re-classified every step.\n"

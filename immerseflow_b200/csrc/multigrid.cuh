@@ -2,7 +2,8 @@
 // Semantics: oracle/ifx_oracle_mg.c (PARITY UNPINNED — the reference always runs point Jacobi, PPESolver.cu:13-31).
 //
 // Level 0 is the solver's grid (padded layout, smoothed by the red-black SOR instantiation of the bulk-copy sweep
-// kernel, kernels_v4.cu).  Level l >= 1 merges 2x2 cells of level l-1 and lives in four dense ghost-inclusive arrays
+// kernel, kernels_v4.cu).  Level l >= 1 merges 2x2 cells of level l-1 (an odd count leaves the last coarse cell of that
+// direction with one child) and lives in four dense ghost-inclusive arrays
 // of (ncx+2) x (ncy+2) doubles: GE / GN = conductance of a cell's east / north face, e = correction, R = right-hand
 // side of the volume-form error equation  sum_f G_f (e_nb - e_C) = R_C.
 #pragma once
@@ -26,12 +27,13 @@ struct MgLevel {
   double* inv_x; double* cp_x; double* inv_y; double* cp_y; double* dp;
 };
 
-// levels for an ncx x ncy grid: halve while both counts are even and >= 4.  Returns the number of levels incl. level 0.
+// levels for an ncx x ncy grid: halve (rounding up: where a count is odd the last coarse cell has a single child) down to
+// 2 cells in one direction.  Returns the number of levels incl. level 0.
 inline int mg_plan(int ncx, int ncy, int* lx, int* ly) {
   int n = 1;
   lx[0] = ncx; ly[0] = ncy;
-  while (n < IFX_MG_MAX_LEVELS && lx[n - 1] % 2 == 0 && ly[n - 1] % 2 == 0 && lx[n - 1] >= 4 && ly[n - 1] >= 4) {
-    lx[n] = lx[n - 1] / 2; ly[n] = ly[n - 1] / 2;
+  while (n < IFX_MG_MAX_LEVELS && lx[n - 1] >= 3 && ly[n - 1] >= 3) {
+    lx[n] = (lx[n - 1] + 1) / 2; ly[n] = (ly[n - 1] + 1) / 2;
     n++;
   }
   return n;

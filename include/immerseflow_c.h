@@ -100,7 +100,7 @@ typedef struct {
    *   3 = red-black SOR with factor ppe_omega;
    *   4 = geometric multigrid, V(2,2) cycles smoothed by red-black SOR — for near-isotropic cells (uniform grids);
    *   5 = geometric multigrid smoothed by the line relaxation of 2 — for the stretched grids the reference ships.
-   * 4 and 5 need even cell counts; an "iteration" of PPE_itermax / ifx_step_stats.ppe_sweeps is then one V-cycle.
+   * For 4 and 5 an "iteration" of PPE_itermax / ifx_step_stats.ppe_sweeps is then one V-cycle.
    * 2, 4 and 5 are single-GPU for now. */
   int ppe_solver;
   double ppe_omega;         /* 0 = take ifx_input.w_PPE (an int in the reference's struct, globalVariables.cuh:26) */

@@ -8,7 +8,8 @@
  * reference's coefficients PPESolver.cu:93-99, zero normal gradient on the grid boundary and on closed faces),
  * so the converged pressure agrees with point Jacobi / red-black SOR to the tolerance; only the path differs.
  *
- * Level 0 is the solver's grid.  Level l+1 merges 2x2 cells of level l (cell counts must be even).  On the
+ * Level 0 is the solver's grid.  Level l+1 merges 2x2 cells of level l, down to 2 cells in one direction; where a
+ * count is odd the last coarse cell of that direction has a single child (1x2, 2x1 or 1x1 cells).  On the
  * coarse levels the error equation is kept in VOLUME form,
  *       sum_faces G_f (e_nb - e_C) = R_C,
  *   G of a fine face      g_e(i,j) = 2 dy_j / (dx_i + dx_ip1)  (= cE * dx_i * dy_j, symmetric), 0 when the face
@@ -58,8 +59,8 @@ void orc_mg_prolong_fine2(int nx, int ny, const unsigned char* ct, int NX, const
 int orc_mg_plan(int ncx, int ncy, int* lx, int* ly) {
   int n = 1;
   lx[0] = ncx; ly[0] = ncy;
-  while (n < ORC_MG_MAX_LEVELS && lx[n - 1] % 2 == 0 && ly[n - 1] % 2 == 0 && lx[n - 1] >= 4 && ly[n - 1] >= 4) {
-    lx[n] = lx[n - 1] / 2; ly[n] = ly[n - 1] / 2;
+  while (n < ORC_MG_MAX_LEVELS && lx[n - 1] >= 3 && ly[n - 1] >= 3) {
+    lx[n] = (lx[n - 1] + 1) / 2; ly[n] = (ly[n - 1] + 1) / 2;      /* odd count: the last coarse cell has one child */
     n++;
   }
   return n;
@@ -94,10 +95,10 @@ static void build_level1(int lines, int nx, int ny, const double* dx, const doub
       const int i = 2 * I, j = 2 * J;          /* children: columns i-1, i; rows j-1, j */
       double ge[2] = {0.0, 0.0}, gn[2] = {0.0, 0.0};
       for (int k = 0; k < 2; k++) {
-        const int jj = j - 1 + k, ii = i - 1 + k;
-        if (i <= nx - 3 && IS_FLUID(ct[ID(i, jj, nx)]) && IS_FLUID(ct[ID(i + 1, jj, nx)]))
+        const int jj = j - 1 + k, ii = i - 1 + k;          /* the second child row / column may not exist (odd count) */
+        if (i <= nx - 3 && jj <= ny - 2 && IS_FLUID(ct[ID(i, jj, nx)]) && IS_FLUID(ct[ID(i + 1, jj, nx)]))
           ge[k] = (2.0 * dy[ID(i, jj, nx)]) / (dx[ID(i, jj, nx)] + dx[ID(i + 1, jj, nx)]);
-        if (j <= ny - 3 && IS_FLUID(ct[ID(ii, j, nx)]) && IS_FLUID(ct[ID(ii, j + 1, nx)]))
+        if (j <= ny - 3 && ii <= nx - 2 && IS_FLUID(ct[ID(ii, j, nx)]) && IS_FLUID(ct[ID(ii, j + 1, nx)]))
           gn[k] = (2.0 * dx[ID(ii, j, nx)]) / (dy[ID(ii, j, nx)] + dy[ID(ii, j + 1, nx)]);
       }
       double ax, ay; dir_scale(lines, ge[0] + ge[1], gn[0] + gn[1], &ax, &ay);
@@ -169,7 +170,7 @@ void orc_mg_restrict_fine(int nx, int ny, const double* dx, const double* dy, co
         const int i = 2 * I - 1 + (k & 1), j = 2 * J - 1 + (k >> 1);
         const int id = ID(i, j, nx);
         r[k] = 0.0;
-        if (!IS_FLUID(ct[id])) continue;
+        if (i > nx - 2 || j > ny - 2 || !IS_FLUID(ct[id])) continue;      /* child beyond the grid (odd count) */
         const double pc = p[id];
         const double pw = (i == 1 || !IS_FLUID(ct[id - 1])) ? pc : p[id - 1];
         const double pe = (i == nx - 2 || !IS_FLUID(ct[id + 1])) ? pc : p[id + 1];

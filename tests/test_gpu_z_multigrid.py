@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("reduce_mode", [ifx.IFX_REDUCE_FUSED, ifx.IFX_REDUCE_REFERENCE])
-@pytest.mark.parametrize("ncx,ncy,body", [(64, 64, False), (96, 64, True), (200, 120, True)])
+@pytest.mark.parametrize("ncx,ncy,body", [(64, 64, False), (96, 64, True), (200, 120, True), (181, 129, True)])
 def test_multigrid_matches_oracle(ncx, ncy, body, reduce_mode):
     xf, yf = ifx.uniform_faces(ncx, ncx / 64.0), ifx.uniform_faces(ncy, ncy / 64.0)
     u0, v0, _ = orc.initial_condition(orc.Grid(xf, yf))
@@ -56,17 +56,17 @@ def test_multigrid_moving_body_rebuilds_the_hierarchy():
     o.close()
 
 
-def test_multigrid_needs_even_cell_counts_and_full_mode():
-    inp = ifx.make_input(51, 64, 1e-3, 150.0)
-    with pytest.raises(ifx.IfxError, match="even cell counts"):
-        ifx.ImmerseFlow(inp, ifx.uniform_faces(51, 1.0), ifx.uniform_faces(64, 1.0), compat=ifx.IFX_COMPAT_FULL, ppe_solver=4)
+def test_multigrid_needs_three_cells_and_full_mode():
+    inp = ifx.make_input(2, 64, 1e-3, 150.0)
+    with pytest.raises(ifx.IfxError, match="at least 3 cells"):
+        ifx.ImmerseFlow(inp, ifx.uniform_faces(2, 1.0), ifx.uniform_faces(64, 1.0), compat=ifx.IFX_COMPAT_FULL, ppe_solver=4)
     inp = ifx.make_input(64, 64, 1e-3, 150.0)
     with pytest.raises(ifx.IfxError, match="IFX_COMPAT_FULL"):
         ifx.ImmerseFlow(inp, ifx.uniform_faces(64, 1.0), ifx.uniform_faces(64, 1.0), ppe_solver=4)
 
 
 @pytest.mark.parametrize("reduce_mode", [ifx.IFX_REDUCE_FUSED, ifx.IFX_REDUCE_REFERENCE])
-@pytest.mark.parametrize("solver,omega,ncx,ncy,itermax", [(5, 1.0, 96, 64, 40), (5, 1.0, 180, 128, 40), (2, 1.8, 32, 24, 3000)])
+@pytest.mark.parametrize("solver,omega,ncx,ncy,itermax", [(5, 1.0, 96, 64, 40), (5, 1.0, 180, 128, 40), (5, 1.0, 75, 51, 40), (2, 1.8, 32, 24, 3000)])
 def test_line_relaxation_and_line_smoothed_multigrid_match_oracle(solver, omega, ncx, ncy, itermax, reduce_mode):
     """PPE_Solver 2 (zebra line SOR, the input file's own "2. Line SOR") and 5 (V-cycle smoothed by it) on a stretched grid
     with two bodies: pressure bit-exact after every step, identical iteration counts."""

@@ -79,7 +79,7 @@ def u8(a):
 
 @pytest.mark.parametrize("lines", [0, 1])
 @pytest.mark.parametrize("ncx,ncy,stretched,bodies", [(64, 32, False, False), (96, 48, True, True), (40, 72, True, True),
-                                                      (50, 50, False, True)])
+                                                      (50, 50, False, True), (61, 35, True, True)])
 def test_mg_kernels_match_oracle_bit_for_bit(shim, ncx, ncy, stretched, bodies, lines):
     L = orc.lib()
     L.orc_mg_create2.restype = C.c_void_p

@@ -57,6 +57,28 @@ def test_multigrid_cycle_count_is_grid_independent_on_square_cells():
     assert max(counts) < 0.2, counts                # ~0.1 per V(2,2) cycle from 32^2 to 256^2
 
 
+@pytest.mark.parametrize("solver,ncx,ncy,stretched", [(4, 181, 129, False), (4, 50, 50, False), (5, 181, 129, True), (5, 75, 50, True)])
+def test_odd_and_awkward_cell_counts_converge_like_powers_of_two(solver, ncx, ncy, stretched):
+    """Coarsening rounds up, so 181 x 129 or the shipped 50 x 50 get a full hierarchy instead of a large coarsest grid:
+    same rate as on 256 x 128."""
+    Lx, Ly = (10.0, 5.0) if stretched else (ncx / 100.0, ncy / 100.0)
+    r = []
+    for k in (2, 8):
+        if stretched:
+            xf, yf = orc.stretched_faces(ncx, Lx, ratio=25 ** (3.0 / ncx)), orc.stretched_faces(ncy, Ly, ratio=12 ** (3.0 / ncy))
+        else:
+            xf, yf = np.linspace(0, Lx, ncx + 1), np.linspace(0, Ly, ncy + 1)
+        s = orc.FullSolver(xf, yf, 1e-2, 100.0, 25, k, ppe_tol=1e-30)
+        g = orc.Grid(xf, yf)
+        X, Y = np.meshgrid(g.xc, g.yc)
+        s.set("u", 1 + 0.3 * np.sin(X) * np.cos(2 * Y)); s.set("v", 0.3 * np.cos(1.3 * X) * np.sin(Y))
+        s.set_bodies([orc.circle_markers(0.4 * Lx, 0.5 * Ly, 0.16 * Ly, 64)])
+        s.update_ib(); s.set_ppe_solver(solver, 1.0)
+        s.predictor()
+        r.append(s.poisson()[4]); s.close()
+    assert (r[1] / r[0]) ** (1.0 / 6.0) < 0.25, r
+
+
 def test_multigrid_never_diverges_on_stretched_grids():
     """Point smoothing cannot be fast on cell aspect ratios of 10+, but the direction-aware coarse scaling keeps the
     cycle contractive (the plain factor 1/2 blows up here)."""
@@ -78,9 +100,12 @@ def test_plan():
     import ctypes as C
     lx, ly = (C.c_int * 16)(), (C.c_int * 16)()
     assert orc.lib().orc_mg_plan(16384, 16384, lx, ly) == 14 and lx[13] == 2
-    assert orc.lib().orc_mg_plan(50, 50, lx, ly) == 2 and (lx[1], ly[1]) == (25, 25)
-    assert orc.lib().orc_mg_plan(51, 64, lx, ly) == 1
     assert orc.lib().orc_mg_plan(4096, 2048, lx, ly) == 11 and (lx[10], ly[10]) == (4, 2)
+    # odd counts round up (the last coarse cell of that direction has one child): any grid coarsens down to 2 cells
+    assert orc.lib().orc_mg_plan(50, 50, lx, ly) == 6 and [lx[k] for k in range(6)] == [50, 25, 13, 7, 4, 2]
+    assert orc.lib().orc_mg_plan(181, 129, lx, ly) == 8 and (lx[7], ly[7]) == (2, 2)
+    assert orc.lib().orc_mg_plan(180, 128, lx, ly) == 7 and (lx[6], ly[6]) == (3, 2)
+    assert orc.lib().orc_mg_plan(2, 64, lx, ly) == 1
 
 
 def stretched_case(ncx, ncy, solver, omega, itermax, tol=1e-30):

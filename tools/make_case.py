@@ -128,7 +128,7 @@ def write_bodies(path: str, bodies) -> None:
 
 
 def build(case: str, out: str, scale: float = 1.0, steps: int = 100):
-    n = lambda c: max(8, int(round(c * scale / 2.0)) * 2)          # even cell counts: the multigrid solvers need them
+    n = lambda c: max(8, int(round(c * scale / 2.0)) * 2)          # even cell counts (any count works; even ones keep every coarse cell 2 x 2)
     os.makedirs(os.path.join(out, "inputs"), exist_ok=True)
     os.makedirs(os.path.join(out, "results"), exist_ok=True)
     os.makedirs(os.path.join(out, "src"), exist_ok=True)
