@@ -205,7 +205,7 @@ def cpu_reference_arm(args, rows: int, steps: int, warmup: int):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import _oracle as orc
     import immerseflow_b200 as ifx
-    ncx, ncy = args.nx, rows
+    ncx, ncy = args.nx, min(rows, args.ny)
     xf = ifx.uniform_faces(ncx, 1.0)
     r0 = 0
     if args.bodies > 0 and args.mode == "full":      # the slab that cuts through the first lattice row of bodies
@@ -277,7 +277,11 @@ def main():
               "workload": f"vortex IC on uniform {args.nx}x{args.ny} cells, reference BCs (u=1,v=0), {body_txt}, "
                           f"dt={args.dt}, Re={args.Re}, AD_itermax={args.ad_itermax}, {args.ppe_sweeps} Poisson sweeps/step from a smooth "
                           f"non-zero pressure field",
-              "grid": [args.nx, args.ny], "l2": "working set 17 GB >> 126 MB L2 (no flush needed)",
+              "grid": [args.nx, args.ny],
+              "l2": "working set %.1f GB of fields vs 126 MB L2 (%s)" % (
+                  8 * 8.0 * (args.nx + 2) * (args.ny + 2) / 1e9,
+                  "inputs larger than L2, no flush needed" if 8 * 8.0 * (args.nx + 2) * (args.ny + 2) > 4 * 126e6
+                  else "NOT larger than L2: an HBM fraction measured on this grid is an L2 figure"),
               "decomposition": f"{world} row slab(s), halo rows by in-kernel NVLink P2P stores, residual by P2P mailboxes"}
 
     if args.impl == "reference":
