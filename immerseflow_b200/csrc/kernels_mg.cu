@@ -373,6 +373,14 @@ static __global__ void k_mg_line_solve(MgLevel lv, int parity, double omega) {
   for (int k0 = 1; k0 < len - 1; k0 += LINE_U) {
     const int n = min(LINE_U, len - 1 - k0);
     double v_inv[LINE_U], v_R[LINE_U], v_ehi[LINE_U], v_elo[LINE_U], v_ec[LINE_U], v_ghi[LINE_U], v_glo[LINE_U], v_ga[LINE_U];
+    if (k0 + LINE_AHEAD + LINE_U <= len - 1) {
+#pragma unroll
+      for (int u = 0; u < LINE_U; u += (DIR == 0 ? 4 : 1)) {
+        const size_t o = (size_t)l * sl + (size_t)(k0 + LINE_AHEAD + u) * sk;
+        line_prefetch(inv_a + o); line_prefetch(lv.R + o); line_prefetch(lv.e + o); line_prefetch(lv.e + o + sc); line_prefetch(lv.e + o - sc);
+        line_prefetch(g_across + o); line_prefetch(g_across + o - sc); line_prefetch(g_along + o - sk);
+      }
+    }
 #pragma unroll
     for (int u = 0; u < LINE_U; u++) {
       if (u < n) {
@@ -397,12 +405,33 @@ static __global__ void k_mg_line_solve(MgLevel lv, int parity, double omega) {
     }
   }
   double xnext = 0.0;
-  for (int k = len - 2; k >= 1; k--) {
-    const size_t o = (size_t)l * sl + (size_t)k * sk;
-    const double x = fma(-cp_a[o], xnext, lv.dp[o]);
-    xnext = x;
-    const double D = (lv.GE[o] + lv.GE[o - 1]) + (lv.GN[o] + lv.GN[o - NX]);
-    if (D > 0.0) { const double ec = lv.e[o]; lv.e[o] = ec + omega * (x - ec); }
+  for (int k1 = len - 2; k1 >= 1; k1 -= LINE_U) {
+    const int n = min(LINE_U, k1);
+    double v_cp[LINE_U], v_dp[LINE_U], v_ec[LINE_U], v_ge[LINE_U], v_gw[LINE_U], v_gn[LINE_U], v_gs[LINE_U];
+    if (k1 - LINE_AHEAD - LINE_U >= 0) {
+#pragma unroll
+      for (int u = 0; u < LINE_U; u += (DIR == 0 ? 4 : 1)) {
+        const size_t o = (size_t)l * sl + (size_t)(k1 - LINE_AHEAD - u) * sk;
+        line_prefetch(cp_a + o); line_prefetch(lv.dp + o); line_prefetch(lv.e + o); line_prefetch(lv.GE + o); line_prefetch(lv.GN + o);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < LINE_U; u++) {
+      if (u < n) {
+        const size_t o = (size_t)l * sl + (size_t)(k1 - u) * sk;
+        v_cp[u] = cp_a[o]; v_dp[u] = lv.dp[o]; v_ec[u] = lv.e[o];
+        v_ge[u] = lv.GE[o]; v_gw[u] = lv.GE[o - 1]; v_gn[u] = lv.GN[o]; v_gs[u] = lv.GN[o - NX];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < LINE_U; u++) {
+      if (u < n) {
+        const double x = fma(-v_cp[u], xnext, v_dp[u]);
+        xnext = x;
+        const double D = (v_ge[u] + v_gw[u]) + (v_gn[u] + v_gs[u]);
+        if (D > 0.0) lv.e[(size_t)l * sl + (size_t)(k1 - u) * sk] = v_ec[u] + omega * (x - v_ec[u]);
+      }
+    }
   }
 }
 
