@@ -47,7 +47,7 @@ extern "C" void ifx_default_options(ifx_options* o) {
   o->rank = 0; o->nranks = 1;
   o->j_begin = 0; o->j_end = 0;        // 0,0 = whole grid
   o->sweeps_per_batch = 64;
-  o->use_graphs = 0;                   // reserved, ignored
+  o->use_graphs = 0;                   // 1: replay the coarse part of the multigrid cycle from a CUDA graph
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -446,6 +446,7 @@ extern "C" int ifx_destroy(ifx_solver* s) {
                     s->d_counters, s->d_rowcount, s->d_rowstart};
   for (int* f : ifields) if (f) cudaFree(f);
   for (double* t : s->tables) cudaFree(t);
+  if (s->mg_graph) cudaGraphExecDestroy(s->mg_graph);
   for (double* q : s->line_f) if (q) cudaFree(q);
   for (int l = 1; l < s->mg_levels; l++) {
     double* a[] = {s->mg[l].GE, s->mg[l].GN, s->mg[l].e, s->mg[l].R, s->mg[l].inv_x, s->mg[l].cp_x, s->mg[l].inv_y, s->mg[l].cp_y,
@@ -1024,6 +1025,36 @@ static int mg_coarse_cycle(ifx_solver* s) {
   return IFX_OK;
 }
 
+// ifx_options.use_graphs: the ~130 small launches of the coarse part are captured once into a CUDA graph and replayed per
+// cycle (the arguments never change: level pointers and omega; only the contents of the arrays do).  Any failure to
+// capture or instantiate switches the option off for the handle and launches directly.
+static int mg_coarse_cycle_maybe_graphed(ifx_solver* s) {
+  if (!s->opt.use_graphs) return mg_coarse_cycle(s);
+  if (!s->mg_graph) {
+    const long long before = s->launches;
+    cudaError_t e = cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal);
+    int rc = IFX_ERR_CUDA;
+    cudaGraph_t g = nullptr;
+    if (e == cudaSuccess) {
+      rc = mg_coarse_cycle(s);
+      e = cudaStreamEndCapture(s->stream, &g);          // also when a launch failed: the stream must leave capture mode
+      if (rc == IFX_OK && e == cudaSuccess && g) e = cudaGraphInstantiate(&s->mg_graph, g, 0);
+      if (g) cudaGraphDestroy(g);
+    }
+    s->mg_graph_launches = s->launches - before;
+    s->launches = before;
+    if (rc != IFX_OK || e != cudaSuccess || !s->mg_graph) {
+      cudaGetLastError();
+      s->mg_graph = nullptr;
+      s->opt.use_graphs = 0;
+      return mg_coarse_cycle(s);
+    }
+  }
+  IFX_CUDA(s, cudaGraphLaunch(s->mg_graph, s->stream));
+  s->launches += s->mg_graph_launches;
+  return IFX_OK;
+}
+
 int ifx::run_ppe_multigrid(ifx_solver* s, ifx_step_stats* st) {
   const Layout& L = s->L;
   if (s->opt.nranks != 1) return fail(s, IFX_ERR_INVALID, "multigrid is single-GPU for now");
@@ -1092,7 +1123,7 @@ int ifx::run_ppe_multigrid(ifx_solver* s, ifx_step_stats* st) {
       }
       s->launches++;
       IFX_CUDA(s, launch_mg_restrict_fine(L, s->M, s->celltype, s->rhs, s->p[base], s->mg[1], s->stream));
-      if ((rc = mg_coarse_cycle(s)) != IFX_OK) return rc;
+      if ((rc = mg_coarse_cycle_maybe_graphed(s)) != IFX_OK) return rc;
       s->launches++;
       IFX_CUDA(s, launch_mg_prolong_fine(L, s->celltype, s->mg[1], s->p[base], 0, s->stream));
       for (int k = 0; k < IFX_MG_NU2; k++) {

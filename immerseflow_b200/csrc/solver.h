@@ -88,6 +88,8 @@ struct ifx_solver {
   int mg_levels = 0;
   ifx::MgLevel mg[IFX_MG_MAX_LEVELS] = {};
   bool mg_valid = false;             // the conductances match the current cell types (cleared by ifx_iblank_update)
+  cudaGraphExec_t mg_graph = nullptr;   // ifx_options.use_graphs: the coarse part of the point-smoothed V-cycle, captured once
+  long long mg_graph_launches = 0;      // kernels one replay stands for
   // fine level of the line relaxation (PPE_Solver 2, 5): stored elimination of the x-lines and of the y-lines
   // (valid for the current cell types: cleared with mg_valid) and the solve's scratch; fields in the layout of p
   double* line_f[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // inv_x, cp_x, inv_y, cp_y, dp

@@ -90,8 +90,10 @@ typedef struct {
   int rank, nranks;
   int j_begin, j_end;
   int sweeps_per_batch;     /* Poisson sweeps enqueued between host looks at the stop flag */
-  int use_graphs;           /* reserved (ignored): sweep batches are plain stream launches; a graph `while` node is
-                               DESIGN.md's next step for launch-bound small grids */
+  int use_graphs;           /* 1: PPE_Solver 4 replays the coarse part of its V-cycle (~130 small launches) from a CUDA graph
+                               captured once per handle; results identical.  0 (default): plain stream launches.
+                               (The sweep loops themselves are plain launches in batches; a graph `while` node for
+                               them is DESIGN.md's next step for launch-bound small grids.) */
   /* Poisson iteration (IFX_COMPAT_FULL).  The reference documents PPE_Solver "1. Point GS, 2. Line
    * SOR" and w-PPE in inputs.txt, parses them (main.cu:42) and always runs point Jacobi.  0 = take
    * ifx_input.PPE_solver (full mode; the reference-compatible mode always runs the reference's Jacobi);

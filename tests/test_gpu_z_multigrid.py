@@ -88,3 +88,23 @@ def test_line_relaxation_and_line_smoothed_multigrid_match_oracle(solver, omega,
             if reduce_mode == ifx.IFX_REDUCE_REFERENCE:
                 assert st.ppe_residual == so[4]
     o.close()
+
+
+@pytest.mark.xfail(strict=False, reason="graph replay of the coarse cycle was written after the round's GPU budget was spent: "
+                                        "not yet run on a GPU (the default path does not use it)")
+def test_multigrid_graph_replay_matches_plain_launches():
+    """ifx_options.use_graphs = 1: same bits, same counts, fewer launches on the stream."""
+    xf, yf = ifx.uniform_faces(128, 2.0), ifx.uniform_faces(64, 1.0)
+    u0, v0, _ = orc.initial_condition(orc.Grid(xf, yf))
+    out = []
+    for graphs in (0, 1):
+        g, o = pair(xf, yf, 1e-3, 150.0, 25, 40, ppe_tol=1e-5, ppe_solver=4, ppe_omega=1.0, use_graphs=graphs)
+        o.close()
+        with g:
+            g.set_bodies([orc.circle_markers(0.6, 0.5, 0.15, 48)])
+            g.initializeData()
+            g.set("u", u0); g.set("v", v0); g.set("p", np.zeros_like(u0))
+            sts = [g.step() for _ in range(3)]
+            out.append(([s.ppe_sweeps for s in sts], g.get("p"), g.get("u")))
+    assert out[0][0] == out[1][0]
+    assert np.array_equal(out[0][1], out[1][1]) and np.array_equal(out[0][2], out[1][2])
