@@ -105,6 +105,19 @@ extern "C" int ifx_set_bodies(ifx_solver* s, int nbodies, const int* offsets, co
     }
     s->h_bbox[4 * b] = x0; s->h_bbox[4 * b + 1] = x1; s->h_bbox[4 * b + 2] = y0; s->h_bbox[4 * b + 3] = y1;
   }
+  // A body that reaches the outermost cell centres would put ghost cells next to the grid boundary, whose image points
+  // leave the grid: the bilinear closure then extrapolates with weights of order 100 and the predictor blows up
+  // (seen on the oracle).  Refuse instead of computing garbage.
+  for (int b = 0; b < nbodies; b++) {
+    const double* bb = s->h_bbox.data() + 4 * b;
+    if (!(bb[0] > s->h_xc[1] && bb[1] < s->h_xc[s->L.nx - 2] && bb[2] > s->h_yc[1] && bb[3] < s->h_yc[s->L.ny - 2])) {
+      s->nbodies = 0;
+      s->h_body_off.assign(1, 0);
+      s->bodies_dirty = true;
+      return fail(s, IFX_ERR_INVALID, "body " + std::to_string(b) + " reaches the outermost cells of the grid (or lies outside): immersed "
+                                      "bodies must stay inside the first / last interior cell centres");
+    }
+  }
   if ((size_t)nm + 1 > s->markers_cap) {
     if (s->d_xm) cudaFree(s->d_xm);
     if (s->d_ym) cudaFree(s->d_ym);

@@ -207,7 +207,9 @@ int ifx_reduce_sum(ifx_solver* s, const double* host, size_t n, double* out);
 /* ---- immersed boundary --------------------------------------------------------------------- */
 /* Bodies are closed polygons of surface markers (counter-clockwise), the 2-D analogue of the
  * predecessor's marker meshes; body b uses markers [offsets[b], offsets[b+1]).  ubody/vbody: rigid
- * velocity of each body (Dirichlet value at the body intercept), may be NULL (= 0). */
+ * velocity of each body (Dirichlet value at the body intercept), may be NULL (= 0).  Bodies must lie strictly inside
+ * the first / last interior cell centres (a body on the grid boundary has ghost cells whose image points leave the
+ * grid); otherwise IFX_ERR_INVALID, and the solver is left without bodies. */
 int ifx_set_bodies(ifx_solver* s, int nbodies, const int* offsets, const double* xm, const double* ym,
                    const double* ubody, const double* vbody);
 /* replaces iBlankComputeKernel (preSim.cu:110-136) + everything the reference lacks: cell

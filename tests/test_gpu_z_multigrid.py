@@ -108,3 +108,17 @@ def test_multigrid_graph_replay_matches_plain_launches():
             out.append(([s.ppe_sweeps for s in sts], g.get("p"), g.get("u")))
     assert out[0][0] == out[1][0]
     assert np.array_equal(out[0][1], out[1][1]) and np.array_equal(out[0][2], out[1][2])
+
+
+def test_bodies_must_lie_inside_the_grid():
+    inp = ifx.make_input(96, 64, 2e-3, 100.0)
+    xf, yf = orc.stretched_faces(96, 4.0, 1.02), orc.stretched_faces(64, 2.0, 1.02)
+    with ifx.ImmerseFlow(inp, xf, yf, compat=ifx.IFX_COMPAT_FULL) as s:
+        s.initializeData()
+        for bad in (orc.circle_markers(0.1, 1.0, 0.3, 64), orc.ellipse_markers(2.0, 1.97, 0.4, 0.1, 0.0, 48),
+                    orc.circle_markers(5.0, 1.0, 0.3, 32)):
+            with pytest.raises(ifx.IfxError, match="outermost cells"):
+                s.set_bodies([orc.circle_markers(1.5, 1.0, 0.3, 32), bad])
+        s.set_bodies([orc.circle_markers(1.5, 1.0, 0.3, 32)])
+        s.iblank_update()
+        assert len(s.ghost_cells()["cell"]) > 0
