@@ -47,6 +47,7 @@ struct Args {
   bool have_bc_u = false, have_bc_v = false;
   double bc_u[4] = {1, 1, 1, 1}, bc_v[4] = {0, 0, 0, 0};      // W, E, S, N
   std::string ic = "vortex";     // vortex | zero | uniform:U,V
+  double ad_tol = 0.0, ppe_tol = 0.0;   // 0: the reference's hard-coded 1e-6 (ADSolver.cu:315, PPESolver.cu:172)
   std::string forces;            // per step and body: pressure and viscous force (ifx_body_forces)
   std::string probes, probe_out; // probe points in, per-step u v p out (ifx_probe)
 };
@@ -69,7 +70,7 @@ static void usage() {
       "            [--mode reference|full] [--bodies FILE] [--steps N] [--write-every-step]\n"
       "            [--reference-log] [--exact-reduction] [--checkpoints] [--restart FILE] [--device K]\n"
       "            [--ppe-solver 1..5] [--ppe-omega W] [--bc-u W,E,S,N] [--bc-v W,E,S,N] [--ic vortex|zero|uniform:U,V]\n"
-      "            [--forces FILE] [--probes FILE --probe-out FILE]\n"
+      "            [--forces FILE] [--probes FILE --probe-out FILE] [--ad-tol T] [--ppe-tol T]\n"
       "  defaults reproduce the reference binary run from src/: ../inputs/inputs.txt, ../inputs/{x,y}grid.dat2,\n"
       "  tmax predictor steps, ../results/{final_results,uc,vc}.dat.  --stretched picks ../inputs/{x,y}grid.dat.\n"
       "  inputs.txt `Write Interval` N: results are (re)written every N steps as well as after the last one; with\n"
@@ -84,6 +85,9 @@ static void usage() {
       "  re-classified every step.\n"
       "  --bc-u / --bc-v: wall values of u and v on the west, east, south, north side (reference: 1,1,1,1 / 0,0,0,0;\n"
       "  lid-driven cavity: --bc-u 0,0,0,1).  --ic: initial condition (reference: its Gaussian vortex).\n"
+      "  --ad-tol / --ppe-tol: stop tolerances of the predictor and Poisson iterations.  The reference hard-codes 1e-6 for\n"
+      "  both and ignores ErrorMax; its residuals are un-normalised sums over all cells, so on large grids 1e-6 is below\n"
+      "  the rounding floor and the loops run to their iteration caps — give a tolerance that scales with the grid.\n"
       "  --forces FILE (full mode): one line per step and body `step time body Fpx Fpy Fvx Fvy`.\n"
       "  --probes FILE: lines `x y`; --probe-out FILE gets one line per step and point `step time k u v p`.\n";
 }
@@ -112,6 +116,8 @@ static Args parse(int argc, char** argv) {
     else if (o == "--bc-u") { if (!four(val(), a.bc_u)) die("--bc-u needs W,E,S,N"); a.have_bc_u = true; }
     else if (o == "--bc-v") { if (!four(val(), a.bc_v)) die("--bc-v needs W,E,S,N"); a.have_bc_v = true; }
     else if (o == "--ic") a.ic = val();
+    else if (o == "--ad-tol") a.ad_tol = std::atof(val().c_str());
+    else if (o == "--ppe-tol") a.ppe_tol = std::atof(val().c_str());
     else if (o == "--forces") a.forces = val();
     else if (o == "--probes") a.probes = val();
     else if (o == "--probe-out") a.probe_out = val();
@@ -147,6 +153,8 @@ int main(int argc, char** argv) {
   opt.ppe_abs_residual = (a.mode == "full") ? 1 : 0;
   opt.ppe_solver = (a.mode == "full") ? a.ppe_solver : 1;       // PPE_Solver / w-PPE (main.cu:42): full mode only
   opt.ppe_omega = a.ppe_omega;
+  if (a.ad_tol > 0.0) opt.ad_tol = a.ad_tol;
+  if (a.ppe_tol > 0.0) opt.ppe_tol = a.ppe_tol;
   opt.bc.u_bc_w = a.bc_u[0]; opt.bc.u_bc_e = a.bc_u[1]; opt.bc.u_bc_s = a.bc_u[2]; opt.bc.u_bc_n = a.bc_u[3];
   opt.bc.v_bc_w = a.bc_v[0]; opt.bc.v_bc_e = a.bc_v[1]; opt.bc.v_bc_s = a.bc_v[2]; opt.bc.v_bc_n = a.bc_v[3];
   ifx_solver* s = nullptr;

@@ -29,7 +29,7 @@ def test_help_lists_every_option(tmp_path):
     assert r.returncode == 0
     for opt in ("--input", "--xgrid", "--ygrid", "--stretched", "--results", "--mode", "--bodies", "--steps", "--write-every-step",
                 "--reference-log", "--exact-reduction", "--checkpoints", "--restart", "--device", "--ppe-solver", "--ppe-omega",
-                "--bc-u", "--bc-v", "--ic", "--forces", "--probes", "--probe-out"):
+                "--bc-u", "--bc-v", "--ic", "--forces", "--probes", "--probe-out", "--ad-tol", "--ppe-tol"):
         assert opt in r.stdout, opt
 
 

@@ -169,7 +169,8 @@ def build(case: str, out: str, scale: float = 1.0, steps: int = 100):
     write_grid(os.path.join(out, "inputs", "xgrid.dat2"), xf)
     write_grid(os.path.join(out, "inputs", "ygrid.dat2"), yf)
     write_inputs(os.path.join(out, "inputs", "inputs.txt"), ncx, ncy, lx, ly, dt, 2.0 * re_phys, steps, 25, 50, solver, 1, steps)
-    cmd = ["immerseflow", "--mode", "full"] + extra
+    # the reference's residuals are un-normalised sums over all cells: a tolerance per cell, times the cell count
+    cmd = ["immerseflow", "--mode", "full", "--ppe-tol", f"{1e-9 * ncx * ncy / dt:.3g}", "--ad-tol", f"{4e-10 * ncx * ncy:.3g}"] + extra      # the reference's 1e-6 on its 52 x 52 case, per cell
     if bodies:
         write_bodies(os.path.join(out, "inputs", "bodies.txt"), bodies)
         cmd += ["--bodies", "../inputs/bodies.txt", "--forces", "../results/forces.dat"]
