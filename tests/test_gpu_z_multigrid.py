@@ -122,3 +122,34 @@ def test_bodies_must_lie_inside_the_grid():
         s.set_bodies([orc.circle_markers(1.5, 1.0, 0.3, 32)])
         s.iblank_update()
         assert len(s.ghost_cells()["cell"]) > 0
+
+
+@pytest.mark.parametrize("name", ["jacobi", "line_sor", "rb_sor", "multigrid_point", "multigrid_line"])
+def test_gpu_reproduces_the_frozen_full_mode_outputs(name, golden_dir):
+    """The CUDA path against a file (tests/golden/full_mode/full_mode.npz: inputs + the oracle's outputs, frozen), for
+    every Poisson solver: cell types, ghost-cell list, u, v, p, body forces, iteration counts."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(golden_dir, "full_mode"))
+    import make_fixtures as mf
+    z = np.load(os.path.join(golden_dir, "full_mode", "full_mode.npz"))
+    solver, omega, itermax, tol = mf.CASES[name]
+    xf, yf = z["xf"], z["yf"]
+    inp = ifx.make_input(mf.NCX, mf.NCY, mf.DT, mf.RE, AD_itermax=mf.AD_ITERMAX, PPE_itermax=itermax)
+    bodies = [z[f"markers{k}"] for k in range(int(z["nbodies"]))]
+    with ifx.ImmerseFlow(inp, xf, yf, compat=ifx.IFX_COMPAT_FULL, ppe_abs_residual=1, ppe_tol=tol, ppe_solver=solver,
+                         ppe_omega=omega) as s:
+        s.set_bodies(bodies, [tuple(v) for v in z["vel"]])
+        s.initializeData()
+        n = s.field_size("u")
+        s.set("u", np.ones(n)); s.set("v", np.zeros(n)); s.set("p", np.zeros(n))
+        counts = []
+        for _ in range(mf.STEPS):
+            st = s.step()
+            counts.append([st.ad_iters, st.ppe_sweeps])
+        assert counts == z[f"{name}/counts"].tolist()
+        assert np.array_equal(s.get("celltype").astype(np.uint8), z[f"{name}/celltype"])
+        assert np.array_equal(s.ghost_cells()["cell"], z[f"{name}/ghost_cells"])
+        for f in ("u", "v", "p"):
+            assert np.array_equal(s.get(f), z[f"{name}/{f}"]), f
+        assert np.array_equal(s.body_forces(len(bodies)), z[f"{name}/forces"])
