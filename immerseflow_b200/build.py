@@ -27,6 +27,7 @@ SOURCES = [
     ("capi.cu", True),
     ("capi_full.cu", True),
     ("capi_ckpt.cu", True),
+    ("capi_mg.cu", True),
     ("kernels_ad.cu", True),
     ("kernels_ppe.cu", True),
     ("kernels_v4.cu", True),

@@ -121,7 +121,8 @@ double rounding_band(const ifx_solver* s, size_t nblocks, int rows_per_cta);
 void fill_bc(const ifx_solver* s, double* two_u, double* two_v);
 int run_ad_loop(ifx_solver* s, ifx_step_stats* st, bool full);
 int run_ppe_loop(ifx_solver* s, ifx_step_stats* st, bool laplace_ref);
-int run_ppe_multigrid(ifx_solver* s, ifx_step_stats* st);
+int enqueue_ppe_sweep(ifx_solver* s, PpeSweepArgs& a, dim3 grid, bool laplace_ref, bool write_res);   // counts the launch
+int run_ppe_multigrid(ifx_solver* s, ifx_step_stats* st);      // capi_mg.cu
 int run_ppe_lines(ifx_solver* s, ifx_step_stats* st);
 int full_refresh_velocity_bc(ifx_solver* s, int buf);
 int full_refresh_pressure_bc(ifx_solver* s, int buf);
