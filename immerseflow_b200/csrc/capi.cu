@@ -183,6 +183,12 @@ int ifx::fetch_small(ifx_solver* s, void* host_pinned, const void* dev, size_t b
   return IFX_OK;
 }
 
+int ifx::check_residual_finite(ifx_solver* s, const char* stage) {
+  if (std::isfinite(s->h_ctl->res0) && std::isfinite(s->h_ctl->res1)) return IFX_OK;
+  return fail(s, IFX_ERR_STATE, std::string(stage) + ": the residual is not finite after iteration " + std::to_string(s->h_ctl->iter) +
+                                " — the solution has diverged (time step too large for the explicit convection, or NaN in the input state)");
+}
+
 int ifx::fetch_ctl(ifx_solver* s) {
   static_assert(sizeof(LoopCtl) % 4 == 0, "LoopCtl is copied in 4-byte words");
   return fetch_small(s, s->h_ctl, s->ctl, sizeof(LoopCtl));
@@ -820,7 +826,7 @@ int ifx::run_ad_loop(ifx_solver* s, ifx_step_stats* st, bool full) {
     st->exact_fallbacks += fallbacks;
     cudaEventElapsedTime(&st->ms_ad, s->ev[0], s->ev[1]);
   }
-  return IFX_OK;
+  return check_residual_finite(s, "predictor");
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -946,5 +952,5 @@ int ifx::run_ppe_loop(ifx_solver* s, ifx_step_stats* st, bool laplace_ref) {
     st->exact_fallbacks += fallbacks;
     cudaEventElapsedTime(&st->ms_ppe, s->ev[2], s->ev[3]);
   }
-  return IFX_OK;
+  return itermax > 0 ? check_residual_finite(s, "Poisson solve") : IFX_OK;
 }

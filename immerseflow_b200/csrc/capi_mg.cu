@@ -200,7 +200,7 @@ int ifx::run_ppe_multigrid(ifx_solver* s, ifx_step_stats* st) {
     st->exact_fallbacks += fallbacks;
     cudaEventElapsedTime(&st->ms_ppe, s->ev[2], s->ev[3]);
   }
-  return IFX_OK;
+  return itermax > 0 ? check_residual_finite(s, "Poisson solve") : IFX_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -332,5 +332,5 @@ int ifx::run_ppe_lines(ifx_solver* s, ifx_step_stats* st) {
     st->exact_fallbacks += fallbacks;
     cudaEventElapsedTime(&st->ms_ppe, s->ev[2], s->ev[3]);
   }
-  return IFX_OK;
+  return itermax > 0 ? check_residual_finite(s, "Poisson solve") : IFX_OK;
 }

@@ -111,6 +111,9 @@ namespace ifx {
 int fail(ifx_solver* s, int code, const std::string& msg);
 // shared by capi.cu and capi_full.cu
 int fetch_ctl(ifx_solver* s);
+// failure detection: a NaN / Inf residual ends every stop rule as "converged" (NaN > tol is false, in the
+// reference too, ADSolver.cu:315); the loops report it instead.  Looks at the control block fetched last.
+int check_residual_finite(ifx_solver* s, const char* stage);
 int fetch_small(ifx_solver* s, void* host_pinned, const void* dev, size_t bytes);   // D2H of a few bytes + stream sync
 int ensure_partials(ifx_solver* s, size_t nblocks);
 int ensure_exact_buffers(ifx_solver* s);

@@ -153,3 +153,17 @@ def test_gpu_reproduces_the_frozen_full_mode_outputs(name, golden_dir):
         for f in ("u", "v", "p"):
             assert np.array_equal(s.get(f), z[f"{name}/{f}"]), f
         assert np.array_equal(s.body_forces(len(bodies)), z[f"{name}/forces"])
+
+
+@pytest.mark.parametrize("compat", [ifx.IFX_COMPAT_REFERENCE, ifx.IFX_COMPAT_FULL])
+def test_nan_in_the_state_is_reported_not_declared_converged(compat, ref_case):
+    """Failure detection: NaN > tol is false, so every stop rule of the reference would end "converged" on a
+    poisoned state; the library returns IFX_ERR_STATE instead."""
+    inp = ifx.make_input(50, 50, 1e-3, 150.0)
+    with ifx.ImmerseFlow(inp, ref_case["xf"], ref_case["yf"], compat=compat) as s:
+        s.initializeData()
+        u = s.get("u")
+        u[52 * 20 + 17] = np.nan
+        s.set("u", u)
+        with pytest.raises(ifx.IfxError, match="not finite"):
+            s.step()

@@ -17,3 +17,4 @@ PYTHONPATH=. timeout 200 python tools/line_mg_bench.py 4096 5 | tee gpurun_out/r
 echo "== default bench (16384 x 16384, pipelined end-to-end)" | tee -a gpurun_out/r2_first.log
 timeout 600 python bench.py > gpurun_out/r2_bench_default.json 2> gpurun_out/r2_bench_default.err
 tail -c 1500 gpurun_out/r2_bench_default.json; tail -3 gpurun_out/r2_bench_default.err
+echo "== sanitizers"; bash tools/sanitize.sh 2>&1 | tee -a gpurun_out/r2_first.log
