@@ -187,7 +187,9 @@ int ifx_save_field(ifx_solver* s, ifx_field f, const char* filename);
 int ifx_checkpoint_write(ifx_solver* s, const char* path, long long step, double time);
 int ifx_checkpoint_read(ifx_solver* s, const char* path, long long* step, double* time);
 
-/* ---- the hot path ------------------------------------------------------------------------- */
+/* ---- the hot path -------------------------------------------------------------------------
+ * Every solve returns IFX_ERR_STATE when the residual it ends on is not finite: NaN > tol is false, so the reference's
+ * stop rules (ADSolver.cu:315, PPESolver.cu:172) would end "converged" on a diverged state. */
 /* replaces ImmerseFlow::ADsolver(), src/include/ADSolver.cu:268-395 (one predictor step; no file I/O) */
 int ifx_ad_solve(ifx_solver* s, ifx_step_stats* stats);
 /* replaces ImmerseFlow::PPESolver(), src/include/PPESolver.cu:137-205 */
