@@ -2,6 +2,8 @@
 // ifx_ad_solve / ifx_ppe_solve / ifx_step between the two compat modes.
 #include "solver.h"
 
+#include <nvtx3/nvToolsExt.h>      // header-only: ranges are no-ops unless a profiler injects its library
+
 #include <algorithm>
 #include <cstring>
 
@@ -60,6 +62,12 @@ int ifx::full_refresh_pressure_bc(ifx_solver* s, int buf) {
   }
   return IFX_OK;
 }
+
+// NVTX range per stage (the reference has no tracing at all): `ncu --nvtx --nvtx-include "ifx:Poisson/"` etc.
+struct StageRange {
+  explicit StageRange(const char* name) { nvtxRangePushA(name); }
+  ~StageRange() { nvtxRangePop(); }
+};
 
 static int require_full(ifx_solver* s, const char* what) {
   if (s->opt.compat != IFX_COMPAT_FULL)
@@ -191,6 +199,7 @@ static int ensure_gc_capacity(ifx_solver* s, int n) {
 // replaces iBlankComputeKernel (preSim.cu:110-136) + the ghost-cell machinery the reference lacks
 extern "C" int ifx_iblank_update(ifx_solver* s, ifx_step_stats* st) {
   if (!s) return IFX_ERR_INVALID;
+  StageRange range("ifx:iblank+ghost-cells");
   int rc = require_full(s, "ifx_iblank_update");
   if (rc != IFX_OK) return rc;
   IFX_CUDA(s, cudaSetDevice(s->device));
@@ -292,6 +301,7 @@ static int full_prepare(ifx_solver* s, ifx_step_stats* st = nullptr) {
 // replaces ImmerseFlow::ADsolver(), ADSolver.cu:268-395
 extern "C" int ifx_ad_solve(ifx_solver* s, ifx_step_stats* st) {
   if (!s) return IFX_ERR_INVALID;
+  StageRange range("ifx:predictor");
   IFX_CUDA(s, cudaSetDevice(s->device));
   if (s->opt.compat == IFX_COMPAT_REFERENCE) return run_ad_loop(s, st, false);
   int rc = require_full(s, "predictor");
@@ -318,6 +328,7 @@ extern "C" int ifx_ad_solve(ifx_solver* s, ifx_step_stats* st) {
 // replaces ImmerseFlow::PPESolver(), PPESolver.cu:137-205
 extern "C" int ifx_ppe_solve(ifx_solver* s, ifx_step_stats* st) {
   if (!s) return IFX_ERR_INVALID;
+  StageRange range("ifx:Poisson");
   IFX_CUDA(s, cudaSetDevice(s->device));
   if (s->opt.compat == IFX_COMPAT_REFERENCE) return run_ppe_loop(s, st, true);
   int rc = require_full(s, "Poisson solve");
@@ -337,6 +348,7 @@ extern "C" int ifx_ppe_solve(ifx_solver* s, ifx_step_stats* st) {
 // the projection the reference leaves empty, AD_PPE_Correction.cu:1-12
 extern "C" int ifx_correct(ifx_solver* s, ifx_step_stats* st) {
   if (!s) return IFX_ERR_INVALID;
+  StageRange range("ifx:projection");
   int rc = require_full(s, "ifx_correct");
   if (rc != IFX_OK) return rc;
   IFX_CUDA(s, cudaSetDevice(s->device));
