@@ -511,6 +511,8 @@ extern "C" int ifx_initialize(ifx_solver* s) {
   s->bodies_dirty = s->nbodies > 0;      // the cell types were just reset to all-fluid
   s->has_gc = false;
   s->gc.count = 0;
+  s->mg_valid = false;               // multigrid hierarchy and line eliminations were built for the old cell types
+  s->line_factor_valid = false;
   s->initialized = true;
   IFX_CUDA(s, cudaStreamSynchronize(s->stream));
   return IFX_OK;
