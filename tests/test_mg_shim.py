@@ -54,7 +54,7 @@ def tables_1d(g):
     return t, arr
 
 
-def case(ncx, ncy, stretched, bodies):
+def case(ncx, ncy, stretched, bodies, seed=None):
     if stretched:
         xf, yf = orc.stretched_faces(ncx, 10.0, ratio=1.03), orc.stretched_faces(ncy, 5.0, ratio=1.02)
     else:
@@ -65,11 +65,16 @@ def case(ncx, ncy, stretched, bodies):
     if bodies:
         offs = np.array([0, 48, 48 + 40], dtype=np.int32)
         m = np.concatenate([orc.circle_markers(4.0, 2.5, 0.9, 48), orc.ellipse_markers(7.0, 1.6, 1.1, 0.35, 0.5, 40)])
+        if seed is not None:          # random bodies, large against small grids: thin fluid gaps, isolated cells, blocked lines
+            r = np.random.default_rng(seed)
+            m = np.concatenate([orc.circle_markers(r.uniform(2, 8), r.uniform(1.5, 3.5), r.uniform(0.5, 1.4), 48),
+                                orc.ellipse_markers(r.uniform(2, 8), r.uniform(1.5, 3.5), r.uniform(0.8, 2.5), r.uniform(0.2, 0.8),
+                                                    r.uniform(0, 3), 40)])
         xm, ym = np.ascontiguousarray(m[:, 0]), np.ascontiguousarray(m[:, 1])
         body_of = np.zeros(N, dtype=np.int32)
         orc.lib().orc_iblank_classify(g.nx, g.ny, P(g.xc), P(g.yc), 2, orc.PI(offs), P(xm), P(ym),
                                       ct.ctypes.data_as(C.POINTER(C.c_ubyte)), orc.PI(body_of))
-        assert (ct != 1).sum() > 20
+        assert seed is not None or (ct != 1).sum() > 20
     return g, ct
 
 
@@ -81,9 +86,27 @@ def u8(a):
 @pytest.mark.parametrize("ncx,ncy,stretched,bodies", [(64, 32, False, False), (96, 48, True, True), (40, 72, True, True),
                                                       (50, 50, False, True), (61, 35, True, True)])
 def test_mg_kernels_match_oracle_bit_for_bit(shim, ncx, ncy, stretched, bodies, lines):
+    check_all_kernels(shim, ncx, ncy, stretched, bodies, lines)
+
+
+def random_shapes():
+    r = np.random.default_rng(2024)
+    out = [(3, 3, 0), (3, 9, 1), (4, 3, 2), (5, 5, 3), (7, 4, 4)]              # the smallest grids multigrid accepts
+    out += [(int(r.integers(5, 45)), int(r.integers(5, 45)), 10 + k) for k in range(19)]
+    return out
+
+
+@pytest.mark.parametrize("ncx,ncy,seed", random_shapes())
+def test_mg_kernels_on_random_shapes_and_bodies(shim, ncx, ncy, seed):
+    """Odd and even cell counts from 3 up, random bodies that are large against the grid (blocked lines, isolated fluid
+    cells, coarse cells with one child): every kernel of the file, both hierarchies, bit for bit against the oracle."""
+    check_all_kernels(shim, ncx, ncy, bool(seed % 2), True, seed % 2, seed=seed)
+
+
+def check_all_kernels(shim, ncx, ncy, stretched, bodies, lines, seed=None):
     L = orc.lib()
     L.orc_mg_create2.restype = C.c_void_p
-    g, ct = case(ncx, ncy, stretched, bodies)
+    g, ct = case(ncx, ncy, stretched, bodies, seed)
     nx, ny, N = g.nx, g.ny, g.nx * g.ny
     lx, ly = (C.c_int * 16)(), (C.c_int * 16)()
     nlev = L.orc_mg_plan(ncx, ncy, lx, ly)
@@ -110,7 +133,7 @@ def test_mg_kernels_match_oracle_bit_for_bit(shim, ncx, ncy, stretched, bodies, 
         else:
             shim.shim_mg_coarsen(lx[l - 1], ly[l - 1], P(GE[l - 1]), P(GN[l - 1]), lx[l], ly[l], P(GE[l]), P(GN[l]), lines)
         assert np.array_equal(GE[l], olevel(l, 0)) and np.array_equal(GN[l], olevel(l, 1)), f"level {l}"
-        if bodies and l == 1:
+        if bodies and l == 1 and seed is None:
             assert (GE[1].reshape(ly[1] + 2, lx[1] + 2)[1:-1, 1:-2] == 0).any()      # closed faces made it to level 1
 
     # ---- residual restriction from the fine level
@@ -166,8 +189,8 @@ def test_mg_kernels_match_oracle_bit_for_bit(shim, ncx, ncy, stretched, bodies, 
         L.orc_ppe_line_pass(nx, ny, P(cP), P(cxm), P(cxp), P(cym), P(cyp), u8(ct), P(rhs), d, par, omega, P(p_o), P(so[0]), P(so[1]))
         shim.shim_line_pass(nx, ny, pitch, tarr, u8(ctp), P(rp), P(pp2), P(ss[0]), P(ss[1]), P(ss[2]), d, par, omega)
         assert np.array_equal(unpad(pp2, nx, ny), p_o), f"fine line pass dir {d} parity {par}"
-    assert not np.array_equal(p_o, p)
-    if bodies:      # a line solve is exact along the line: the residual of the rows just relaxed with omega = 1 vanishes there
+    assert seed is not None or not np.array_equal(p_o, p)
+    if bodies and seed is None:      # a line solve is exact along the line: the residual of the rows just relaxed with omega = 1 vanishes there
         q_o = p.copy()
         L.orc_ppe_line_pass(nx, ny, P(cP), P(cxm), P(cxp), P(cym), P(cyp), u8(ct), P(rhs), 0, 1, C.c_double(1.0), P(q_o), P(so[0]), P(so[1]))
         res = np.zeros(N); scratch = np.zeros(N)
