@@ -153,3 +153,31 @@ def test_line_solvers_reach_the_same_pressure_as_sor():
         assert np.abs(d - d.mean()).max() < 1e-7
     for s in (a, b, c):
         s.close()
+
+
+def test_cycles_contract_on_random_grids_and_bodies():
+    """Robustness sweep: random cell counts (odd, even, down to 6), uniform square cells for the point-smoothed cycle and
+    aggressively stretched grids for the line-smoothed one, two random bodies: no divergence, and a useful rate everywhere
+    (worst seen in a 40-case sweep: 0.38 for solver 4, 0.62 for solver 5 at a per-cell stretching ratio of 1.19)."""
+    r = np.random.default_rng(7)
+    for k in range(12):
+        ncx, ncy = int(r.integers(6, 140)), int(r.integers(6, 140))
+        stretched = bool(k % 2)
+        Lx = 10.0
+        Ly = 5.0 if stretched else 10.0 * ncy / ncx
+        xf = orc.stretched_faces(ncx, Lx, ratio=20 ** (3.0 / ncx)) if stretched else np.linspace(0, Lx, ncx + 1)
+        yf = orc.stretched_faces(ncy, Ly, ratio=10 ** (3.0 / ncy)) if stretched else np.linspace(0, Ly, ncy + 1)
+        bodies = [orc.circle_markers(r.uniform(0.3, 0.7) * Lx, r.uniform(0.3, 0.7) * Ly, r.uniform(0.05, 0.2) * min(Lx, Ly), 48),
+                  orc.ellipse_markers(r.uniform(0.25, 0.75) * Lx, r.uniform(0.25, 0.75) * Ly, r.uniform(0.05, 0.25) * Lx,
+                                      r.uniform(0.03, 0.1) * Ly, r.uniform(0, 3), 40)]
+        solver = 5 if stretched else 4
+        res = []
+        for it in (1, 7):
+            s = orc.FullSolver(xf, yf, 1e-2, 100.0, 25, it, ppe_tol=1e-30)
+            g = orc.Grid(xf, yf)
+            X, Y = np.meshgrid(g.xc, g.yc)
+            s.set("u", 1 + 0.3 * np.sin(X) * np.cos(2 * Y)); s.set("v", 0.3 * np.cos(1.3 * X) * np.sin(Y))
+            s.set_bodies(bodies); s.update_ib(); s.set_ppe_solver(solver, 1.0)
+            s.predictor()
+            res.append(s.poisson()[4]); s.close()
+        assert (res[1] / res[0]) ** (1.0 / 6.0) < 0.75, (solver, ncx, ncy, res)
