@@ -167,3 +167,39 @@ def test_nan_in_the_state_is_reported_not_declared_converged(compat, ref_case):
         s.set("u", u)
         with pytest.raises(ifx.IfxError, match="not finite"):
             s.step()
+
+
+def test_zero_copy_control_and_async_transfers_change_nothing():
+    """ifx_options.zero_copy_control moves the step's few-byte control traffic through host-mapped memory instead of
+    cudaMemcpyAsync, ifx_set/get_field_async drop the wait: same bits, same counts (bench.py's end-to-end pipeline
+    relies on both)."""
+    xf, yf = orc.stretched_faces(96, 4.0, 1.02), orc.stretched_faces(64, 2.0, 1.02)
+    inp = ifx.make_input(96, 64, 2e-3, 100.0, AD_itermax=25, PPE_itermax=120)
+    out = []
+    for zc in (0, 1):
+        with ifx.ImmerseFlow(inp, xf, yf, compat=ifx.IFX_COMPAT_FULL, ppe_abs_residual=1, zero_copy_control=zc) as s:
+            s.initializeData()
+            n = s.field_size("u")
+            u0, v0, p0 = np.ones(n), np.zeros(n), np.zeros(n)
+            if zc:      # upload without waiting; the step that follows is ordered behind the copies on the handle's stream
+                for name, a in (("u", u0), ("v", v0), ("p", p0)):
+                    s.set_async(name, a)
+            else:
+                s.set("u", u0); s.set("v", v0); s.set("p", p0)
+            counts = []
+            for step in range(3):
+                s.set_bodies([orc.circle_markers(1.5 + 0.02 * step, 1.0, 0.3, 64)], [(0.2, 0.0)])
+                st = s.step()
+                counts.append((st.ad_iters, st.ppe_sweeps))
+            if zc:
+                got = {k: np.empty(n) for k in ("u", "v", "p")}
+                for k in got:
+                    s.get_async(k, got[k])
+                s.synchronize()
+            else:
+                got = {k: s.get(k) for k in ("u", "v", "p")}
+            out.append((counts, got, s.ghost_cells()["cell"]))
+    assert out[0][0] == out[1][0]
+    assert np.array_equal(out[0][2], out[1][2])
+    for k in ("u", "v", "p"):
+        assert np.array_equal(out[0][1][k], out[1][1][k]), k

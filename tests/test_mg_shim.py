@@ -1,6 +1,6 @@
 """Multigrid transfer / coarse-level kernels (immerseflow_b200/csrc/kernels_mg.cu) compiled as plain C++ through
 tests/shim/cuda_host_shim.h and run, launch grid and all, on the CPU — every kernel bit for bit against the oracle
-(oracle/ifx_oracle_mg.c).  The GPU run of the same source is tests/test_gpu_z_multigrid.py."""
+(oracle/ifx_oracle_mg.c).  The GPU run of the same source is tests/test_gpu_z_late_round.py."""
 import ctypes as C
 import os
 import sys
