@@ -367,10 +367,11 @@ def main():
     sampler.start()
     l0 = s.launch_count
     t0 = time.perf_counter()
-    ad_ms, ppe_ms, cor_ms, ib_ms, k_ad, k_ppe = [], [], [], [], 0, 0
+    ad_ms, ppe_ms, cor_ms, ib_ms, sweep_ms, k_ad, k_ppe = [], [], [], [], [], 0, 0
     for _ in range(args.steps):
         a, b = one_step()
         ad_ms.append(a.ms_ad); ppe_ms.append(b.ms_ppe); cor_ms.append(b.ms_correct); ib_ms.append(b.ms_ib)
+        sweep_ms.append(a.ms_ad_sweeps)
         k_ad, k_ppe = a.ad_iters, b.ppe_sweeps
     barrier()
     wall = time.perf_counter() - t0
@@ -390,7 +391,9 @@ def main():
     # ---- roofline of the dominant kernel (k_ad_jacobi: 25 launches/step vs ~51 Poisson launches of 1/3 the bytes)
     peak, peak_src = peaks()
     cells_local = ncx * (je - jb)
-    ad_launch_ms = float(np.mean(ad_ms)) / (k_ad + 2.0) if k_ad else None   # + source pass (measured ~2 sweeps, profiles/)
+    # CUDA events around the k_ad sweep launches alone (ifx_step_stats.ms_ad_sweeps; with bodies the per-iteration
+    # ghost-cell kernels, a few microseconds each, are inside)
+    ad_launch_ms = float(np.mean(sweep_ms)) / k_ad if k_ad else None
     jac_bytes = 49.0 * cells_local               # read u,v,sx,sy + write u',v' (48 B/cell) + 1 B cell type
     ppe_launch_ms = float(np.mean(ppe_ms)) / (k_ppe + 1)
     ppe_b_cell = 25 if full else 16              # full: read p, rhs, cell type; write p' — reference Laplace: read p, write p'

@@ -21,7 +21,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # IFX_LIBRARY: explicit path of a build of the same C-ABI (kernel experiments, tools/build_variant.sh)
 LIB_PATH = os.environ.get("IFX_LIBRARY") or os.path.join(_HERE, "libimmerseflow_b200.so")
 
-IFX_ABI_VERSION = 1
+IFX_ABI_VERSION = 2
 IFX_COMPAT_REFERENCE, IFX_COMPAT_FULL = 0, 1
 IFX_REDUCE_FUSED, IFX_REDUCE_REFERENCE = 0, 1
 
@@ -73,7 +73,7 @@ class IfxStepStats(C.Structure):
     _fields_ = [("ad_iters", C.c_int), ("ad_ures", C.c_double), ("ad_vres", C.c_double),
                 ("ppe_sweeps", C.c_int), ("ppe_residual", C.c_double), ("exact_fallbacks", C.c_int),
                 ("ms_ad", C.c_float), ("ms_ppe", C.c_float), ("ms_correct", C.c_float), ("ms_ib", C.c_float),
-                ("ms_total", C.c_float)]
+                ("ms_total", C.c_float), ("ms_ad_sweeps", C.c_float)]
 
 
 class IfxError(RuntimeError):
@@ -200,6 +200,7 @@ class StepStats:
     ms_correct: float = 0.0
     ms_ib: float = 0.0
     ms_total: float = 0.0
+    ms_ad_sweeps: float = 0.0
 
     @classmethod
     def from_c(cls, s: IfxStepStats) -> "StepStats":

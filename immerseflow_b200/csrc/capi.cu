@@ -731,6 +731,7 @@ int ifx::run_ad_loop(ifx_solver* s, ifx_step_stats* st, bool full) {
   s->launches++;
 
   IFX_CUDA(s, cudaMemsetAsync(s->ctl, 0, sizeof(LoopCtl), s->stream));
+  IFX_CUDA(s, cudaEventRecord(s->ev[8], s->stream));        // from here to ev[9]: the Jacobi sweeps (+ ghost-cell kernels)
   if (itermax <= 0) {   // while-condition false on entry: zero iterations (ADSolver.cu:315)
     if (st) { st->ad_iters = 0; st->ad_ures = 1.0; st->ad_vres = 1.0; }
     IFX_CUDA(s, cudaStreamSynchronize(s->stream));
@@ -810,6 +811,7 @@ int ifx::run_ad_loop(ifx_solver* s, ifx_step_stats* st, bool full) {
     if (m >= itermax) return fail(s, IFX_ERR_STATE, "predictor loop ran past AD_itermax without a decision");
     batch = 2;
   }
+  IFX_CUDA(s, cudaEventRecord(s->ev[9], s->stream));
   const int K = s->h_ctl->iter;
   s->cur_uv = (base + K) & 1;
   s->last_ad_iters = K;
@@ -827,6 +829,7 @@ int ifx::run_ad_loop(ifx_solver* s, ifx_step_stats* st, bool full) {
     st->ad_vres = s->h_ctl->res1;
     st->exact_fallbacks += fallbacks;
     cudaEventElapsedTime(&st->ms_ad, s->ev[0], s->ev[1]);
+    cudaEventElapsedTime(&st->ms_ad_sweeps, s->ev[8], s->ev[9]);
   }
   return check_residual_finite(s, "predictor");
 }

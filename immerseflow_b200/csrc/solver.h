@@ -102,7 +102,7 @@ struct ifx_solver {
   int rows_override = 0;             // IFX_ROWS_PER_CTA
   int last_ad_iters = 5;
   double ad_hist[2 * 64] = {};       // (uRes, vRes) per iteration of the last predictor solve
-  cudaEvent_t ev[8] = {};
+  cudaEvent_t ev[10] = {};           // stage timers; [8], [9]: the Jacobi sweeps of the predictor alone
   long long launches = 0;
   std::string err;
 };

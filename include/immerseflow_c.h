@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define IFX_ABI_VERSION 1
+#define IFX_ABI_VERSION 2
 
 typedef enum {
   IFX_OK = 0,
@@ -123,6 +123,8 @@ typedef struct {
   double ppe_residual;
   int exact_fallbacks;      /* stop decisions that had to be re-evaluated in reference order */
   float ms_ad, ms_ppe, ms_correct, ms_ib, ms_total;   /* CUDA-event stage timings */
+  float ms_ad_sweeps;       /* of ms_ad, the Jacobi sweeps alone (ad_iters launches + their ghost-cell kernels): what a
+                               per-launch bandwidth of the predictor sweep is computed from */
 } ifx_step_stats;
 
 typedef enum {
