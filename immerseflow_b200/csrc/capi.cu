@@ -119,8 +119,8 @@ static int build_metrics(ifx_solver* s, const double* xf, const double* yf) {
 
 // columns per CTA tile of the sweep kernels (mode 0: Poisson, 2: predictor)
 static int tile_cols_for(const ifx_solver* s, int mode) {
-  const int tune = (mode == 2) ? s->tune_ad : s->tune_ppe;
-  return s->kernel_variant == 4 ? v4_tile_cols(mode, tune) : TILE_COLS;
+  (void)s;
+  return v4_tile_cols(mode);
 }
 
 int ifx::rows_per_cta_for(const ifx_solver* s, int mode) {
@@ -361,9 +361,6 @@ extern "C" int ifx_create(const ifx_input* in, const double* xf, const double* y
   s->in = *in;
   s->opt = opt;
   s->device = opt.device;
-  if (const char* e = std::getenv("IFX_KERNEL_VARIANT")) { const int v = std::atoi(e); if (v == 1 || v == 4) s->kernel_variant = v; }
-  if (const char* e = std::getenv("IFX_TUNE_AD")) s->tune_ad = std::atoi(e);
-  if (const char* e = std::getenv("IFX_TUNE_PPE")) s->tune_ppe = std::atoi(e);
   if (const char* e = std::getenv("IFX_ROWS_PER_CTA")) s->rows_override = std::atoi(e);
   auto bail = [&](int code) { g_create_error = s->err; ifx_destroy(s); return code; };
 
@@ -668,8 +665,7 @@ extern "C" int ifx_reduce_sum(ifx_solver* s, const double* host, size_t n, doubl
 // ------------------------------------------------------------------------------------------------
 static int launch_ad_jacobi(ifx_solver* s, AdJacobiArgs& a, dim3 grid, bool write_res) {
   s->launches++;
-  if (s->kernel_variant == 1) IFX_CUDA(s, ifx::launch_ad_jacobi(a, grid, s->stream, write_res, s->has_gc));
-  else IFX_CUDA(s, ifx::launch_ad_jacobi_v4(a, grid, s->stream, write_res, s->tune_ad));
+  IFX_CUDA(s, ifx::launch_ad_jacobi_v4(a, grid, s->stream, write_res));
   return IFX_OK;
 }
 
@@ -705,9 +701,8 @@ int ifx::run_ad_loop(ifx_solver* s, ifx_step_stats* st, bool full) {
   IFX_CUDA(s, cudaEventRecord(s->ev[0], s->stream));
   const int base = s->cur_uv;
   const bool slabs = s->connected && s->opt.nranks > 1;
-  const int tw_ad = v4_tile_cols(2, s->tune_ad);
+  const int tw_ad = v4_tile_cols(2);
   if (slabs) {   // halo rows of the starting field (also what the source pass reads)
-    if (s->kernel_variant != 4) return fail(s, IFX_ERR_INVALID, "slabs need the default kernel variant");
     const int fi[2] = {base, 2 + base};
     if ((rc = halo_exchange(s, 0, 2, fi, tw_ad)) != IFX_OK) return rc;
   }
@@ -839,8 +834,7 @@ int ifx::run_ad_loop(ifx_solver* s, ifx_step_stats* st, bool full) {
 // ------------------------------------------------------------------------------------------------
 int ifx::enqueue_ppe_sweep(ifx_solver* s, PpeSweepArgs& a, dim3 grid, bool laplace_ref, bool write_res) {
   s->launches++;
-  if (s->kernel_variant == 1) IFX_CUDA(s, ifx::launch_ppe_sweep(a, grid, s->stream, laplace_ref, write_res, s->has_gc));
-  else IFX_CUDA(s, ifx::launch_ppe_sweep_v4(a, grid, s->stream, laplace_ref, write_res, s->tune_ppe));
+  IFX_CUDA(s, ifx::launch_ppe_sweep_v4(a, grid, s->stream, laplace_ref, write_res));
   return IFX_OK;
 }
 
@@ -859,8 +853,7 @@ int ifx::run_ppe_loop(ifx_solver* s, ifx_step_stats* st, bool laplace_ref) {
   IFX_CUDA(s, cudaEventRecord(s->ev[2], s->stream));
   const int base = s->cur_p;
   const bool slabs = s->connected && s->opt.nranks > 1;
-  const int tw_ppe = v4_tile_cols(laplace_ref ? 0 : 1, s->tune_ppe);
-  if (slabs && s->kernel_variant != 4) return fail(s, IFX_ERR_INVALID, "slabs need the default kernel variant");
+  const int tw_ppe = v4_tile_cols(laplace_ref ? 0 : 1);
   if (laplace_ref) {
     // set_pressure_BC (PPESolver.cu:164); the ring is then carried through every sweep (:21)
     s->launches += 2;

@@ -16,7 +16,9 @@ using namespace ifx;
 namespace {
 struct CkptHeader {
   char magic[8];                 // "IFXCKPT1"
-  int abi, compat, nx, ny, j_begin, j_end, rank, nranks, nfields, reserved;
+  int abi, compat, nx, ny, j_begin, j_end, rank, nranks, nfields;
+  int faces_valid;               // 1: uf, vf are the projected face velocities; 0: they are not state (before the first
+                                 // step, after ifx_set_field(u/v), after the bodies moved) and the reader ignores them
   long long step;
   double time;
 };
@@ -34,6 +36,7 @@ extern "C" int ifx_checkpoint_write(ifx_solver* s, const char* path, long long s
   std::memcpy(h.magic, kMagic, 8);
   h.abi = IFX_ABI_VERSION; h.compat = s->opt.compat; h.nx = s->L.nx; h.ny = s->L.ny;
   h.j_begin = s->L.jb; h.j_end = s->L.je; h.rank = s->opt.rank; h.nranks = s->opt.nranks; h.nfields = nf;
+  h.faces_valid = (full && s->faces_valid) ? 1 : 0;
   h.step = step; h.time = time;
   bool ok = std::fwrite(&h, sizeof(h), 1, fp) == 1;
   std::vector<double> buf;
@@ -62,23 +65,33 @@ extern "C" int ifx_checkpoint_read(ifx_solver* s, const char* path, long long* s
   if (h.compat != s->opt.compat) return bad("written in the other compat mode");
   const int want = s->opt.compat == IFX_COMPAT_FULL ? 5 : 3;
   if (h.nfields != want) return bad("unexpected field count");
+  if (h.abi != IFX_ABI_VERSION) return bad("written by another version of the library");
+  if (h.rank != s->opt.rank || h.nranks != s->opt.nranks) return bad("written by another rank / for another number of slabs");
+  // the whole file is read and validated before any of it is applied: a truncated or foreign file leaves the state alone
+  const ifx_field fields[5] = {IFX_FIELD_U, IFX_FIELD_V, IFX_FIELD_P, IFX_FIELD_UF, IFX_FIELD_VF};
+  std::vector<std::vector<double>> data(h.nfields);
+  for (int k = 0; k < h.nfields; k++) {      // order in the file: u, v, p, then uf, vf
+    int id; unsigned long long n;
+    if (std::fread(&id, sizeof(id), 1, fp) != 1 || std::fread(&n, sizeof(n), 1, fp) != 1) return bad("truncated");
+    if (id != (int)fields[k]) return bad("fields out of order");
+    if (n != ifx_field_size(s, fields[k])) return bad("field size mismatch");
+    data[k].resize(n);
+    if (std::fread(data[k].data(), sizeof(double), n, fp) != n) return bad("truncated");
+  }
+  std::fclose(fp);
   // bodies set but not classified yet: classify first — ifx_iblank_update invalidates the face velocities (closed
   // faces move with the bodies), which must not happen after the file's faces have been put in place
   if (s->bodies_dirty) {
     const int rc = ifx_iblank_update(s, nullptr);
-    if (rc != IFX_OK) { std::fclose(fp); return rc; }
+    if (rc != IFX_OK) return rc;
   }
-  std::vector<double> buf;
-  for (int k = 0; k < h.nfields; k++) {      // order in the file: u, v, p, then uf, vf (faces after cells: ifx_set_field
-    int id; unsigned long long n;            // invalidates the faces when cell velocities are set)
-    if (std::fread(&id, sizeof(id), 1, fp) != 1 || std::fread(&n, sizeof(n), 1, fp) != 1) return bad("truncated");
-    if (n != ifx_field_size(s, (ifx_field)id)) return bad("field size mismatch");
-    buf.resize(n);
-    if (std::fread(buf.data(), sizeof(double), n, fp) != n) return bad("truncated");
-    const int rc = ifx_set_field(s, (ifx_field)id, buf.data(), n);
-    if (rc != IFX_OK) { std::fclose(fp); return rc; }
+  // faces after cells (ifx_set_field invalidates the faces when cell velocities are set), and only if they were state
+  // when the file was written: otherwise the next predictor rebuilds them from the cells, as the unbroken run does
+  for (int k = 0; k < h.nfields; k++) {
+    if (k >= 3 && !h.faces_valid) break;
+    const int rc = ifx_set_field(s, fields[k], data[k].data(), data[k].size());
+    if (rc != IFX_OK) return rc;
   }
-  std::fclose(fp);
   if (step) *step = h.step;
   if (time) *time = h.time;
   return IFX_OK;

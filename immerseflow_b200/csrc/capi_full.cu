@@ -72,7 +72,6 @@ struct StageRange {
 static int require_full(ifx_solver* s, const char* what) {
   if (s->opt.compat != IFX_COMPAT_FULL)
     return fail(s, IFX_ERR_INVALID, std::string(what) + " requires IFX_COMPAT_FULL (the reference has no such stage)");
-  if (s->kernel_variant != 4) return fail(s, IFX_ERR_INVALID, "IFX_COMPAT_FULL needs the default kernel variant");
   return IFX_OK;
 }
 

@@ -20,18 +20,29 @@ static int mg_ensure(ifx_solver* s) {
     int lx[IFX_MG_MAX_LEVELS], ly[IFX_MG_MAX_LEVELS];
     const int n = mg_plan(s->L.nx - 2, s->L.ny - 2, lx, ly);
     if (n < 2) return fail(s, IFX_ERR_INVALID, "multigrid needs at least 3 cells in both directions");
-    for (int l = 1; l < n; l++) {
+    // all or nothing: a hierarchy that stops short of the plan would converge differently from the oracle's
+    cudaError_t e = cudaSuccess;
+    for (int l = 1; l < n && e == cudaSuccess; l++) {
       const size_t bytes = sizeof(double) * (size_t)(lx[l] + 2) * (ly[l] + 2);
       s->mg[l].ncx = lx[l]; s->mg[l].ncy = ly[l];
       double** a[] = {&s->mg[l].GE, &s->mg[l].GN, &s->mg[l].e, &s->mg[l].R, &s->mg[l].inv_x, &s->mg[l].cp_x, &s->mg[l].inv_y,
                       &s->mg[l].cp_y, &s->mg[l].dp};
       const int narr = s->opt.ppe_solver == 5 ? 9 : 4;       // line-elimination storage only for the line smoother
-      for (int q = 0; q < narr; q++) {
-        IFX_CUDA(s, cudaMalloc(a[q], bytes));
-        IFX_CUDA(s, cudaMemsetAsync(*a[q], 0, bytes, s->stream));
+      for (int q = 0; q < narr && e == cudaSuccess; q++) {
+        e = cudaMalloc(a[q], bytes);
+        if (e == cudaSuccess) e = cudaMemsetAsync(*a[q], 0, bytes, s->stream);
       }
-      s->mg_levels = l + 1;          // what ifx_destroy frees if a later allocation fails
     }
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      for (int l = 1; l < n; l++) {
+        double** a[] = {&s->mg[l].GE, &s->mg[l].GN, &s->mg[l].e, &s->mg[l].R, &s->mg[l].inv_x, &s->mg[l].cp_x, &s->mg[l].inv_y,
+                        &s->mg[l].cp_y, &s->mg[l].dp};
+        for (double** q : a) { if (*q) cudaFree(*q); *q = nullptr; }
+      }
+      return fail(s, IFX_ERR_CUDA, std::string("multigrid hierarchy: ") + cudaGetErrorString(e));
+    }
+    s->mg_levels = n;
     s->mg_valid = false;
   }
   if (!s->mg_valid) {
@@ -116,7 +127,6 @@ static int mg_coarse_cycle_maybe_graphed(ifx_solver* s) {
 int ifx::run_ppe_multigrid(ifx_solver* s, ifx_step_stats* st) {
   const Layout& L = s->L;
   if (s->opt.nranks != 1) return fail(s, IFX_ERR_INVALID, "multigrid is single-GPU for now");
-  if (s->kernel_variant != 4) return fail(s, IFX_ERR_INVALID, "multigrid needs the default kernel variant");
   const bool exact = s->opt.reduce_mode == IFX_REDUCE_REFERENCE;
   const int itermax = s->in.PPE_itermax;
   const int ry = rows_per_cta_for(s, 1);
@@ -216,7 +226,6 @@ int ifx::run_ppe_lines(ifx_solver* s, ifx_step_stats* st) {
   const Layout& L = s->L;
   const bool mg = s->opt.ppe_solver == 5;
   if (s->opt.nranks != 1) return fail(s, IFX_ERR_INVALID, "line relaxation is single-GPU for now");
-  if (s->kernel_variant != 4) return fail(s, IFX_ERR_INVALID, "line relaxation needs the default kernel variant");
   const bool exact = s->opt.reduce_mode == IFX_REDUCE_REFERENCE;
   const int itermax = s->in.PPE_itermax;
   const int ry = rows_per_cta_for(s, 1);

@@ -160,19 +160,16 @@ __device__ __forceinline__ void block_reduce_and_decide(double r0, double r1, do
 // Host-side launchers.  Every __global__ is launched from the translation unit that defines it.
 // ---------------------------------------------------------------------------------------------
 // kernels_ad.cu
-cudaError_t launch_ad_jacobi(const AdJacobiArgs& a, dim3 grid, cudaStream_t st, bool write_res, bool has_gc);
 enum AdSourceVariant { SRC_REF_VF_ZERO = 0, SRC_REF_VF_ARRAY = 1, SRC_FACES = 2 };
 cudaError_t launch_ad_source(const AdSourceArgs& a, dim3 grid, cudaStream_t st, AdSourceVariant v);
 cudaError_t launch_copy_ring(const Layout& L, const double* s0, double* d0, const double* s1, double* d1,
                              cudaStream_t st);
 // kernels_ppe.cu
-cudaError_t launch_ppe_sweep(const PpeSweepArgs& a, dim3 grid, cudaStream_t st, bool laplace_ref, bool write_res,
-                             bool has_gc);
 cudaError_t launch_set_pressure_bc_ref(const Layout& L, double* p0, double* p1, cudaStream_t st);
-// kernels_v4.cu — v3 + lean interior path, in-line shared-reciprocal division, smem row tables (default)
-cudaError_t launch_ad_jacobi_v4(const AdJacobiArgs& a, dim3 grid, cudaStream_t st, bool write_res, int tune);
-cudaError_t launch_ppe_sweep_v4(const PpeSweepArgs& a, dim3 grid, cudaStream_t st, bool laplace_ref, bool write_res, int tune);
-int v4_tile_cols(int mode /*0,1: Poisson, 2: predictor*/, int tune);
+// kernels_v4.cu — the sweep kernels: bulk-copy row pipeline, lean interior path, in-line shared-reciprocal division
+cudaError_t launch_ad_jacobi_v4(const AdJacobiArgs& a, dim3 grid, cudaStream_t st, bool write_res);
+cudaError_t launch_ppe_sweep_v4(const PpeSweepArgs& a, dim3 grid, cudaStream_t st, bool laplace_ref, bool write_res);
+int v4_tile_cols(int mode /*0: Laplace, 1: general Poisson, 2: predictor*/);
 // kernels_full.cu — PPE source term, projection, BC refresh (IFX_COMPAT_FULL)
 cudaError_t launch_apply_ring(const Layout& L, double* q, const double* two_bc, int neumann, cudaStream_t st);
 cudaError_t launch_faces_init(const Layout& L, const Metrics& M, const uint8_t* ct, const double* ub, const double* vb,

@@ -95,10 +95,6 @@ struct ifx_solver {
   double* line_f[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // inv_x, cp_x, inv_y, cp_y, dp
   bool line_factor_valid = false;
 
-  int kernel_variant = 4;            // 1: register-rolled direct loads (kernels_ad.cu / kernels_ppe.cu, reference mode only)
-                                     // 4: bulk-copy row pipeline, lean interior path (kernels_v4.cu, default)
-                                     // (IFX_KERNEL_VARIANT; variants 2, 3 were stepping stones, see profiles/)
-  int tune_ad = 0, tune_ppe = 0;     // pipeline geometry selectors (IFX_TUNE_AD / IFX_TUNE_PPE)
   int rows_override = 0;             // IFX_ROWS_PER_CTA
   int last_ad_iters = 5;
   double ad_hist[2 * 64] = {};       // (uRes, vRes) per iteration of the last predictor solve

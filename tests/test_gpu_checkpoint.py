@@ -50,9 +50,33 @@ def _run(mode, tmp_path, split):
 
 
 @pytest.mark.parametrize("mode", ["reference", "full"])
-@pytest.mark.parametrize("split", [1, 3])
+@pytest.mark.parametrize("split", [0, 1, 3])      # 0: saved before the first step — the face velocities are not state yet
 def test_restart_is_bit_identical(mode, split, tmp_path):
     _run(mode, tmp_path, split)
+
+
+def test_checkpoint_taken_after_the_bodies_moved_ignores_the_stale_faces(tmp_path):
+    """After ifx_iblank_update with moved bodies the stored uf, vf are stale (closed faces moved): a file written then
+    must not restore them as valid — the continued run rebuilds them from the cells, like the unbroken run."""
+    ncx, ncy = 140, 90
+    xf, yf = orc.stretched_faces(ncx, 4.0, 1.02), orc.stretched_faces(ncy, 2.0, 1.02)
+    inp = ifx.make_input(ncx, ncy, 1e-3, 150.0, AD_itermax=12, PPE_itermax=40)
+    kw = dict(compat=ifx.IFX_COMPAT_FULL, ppe_abs_residual=1)
+    b0, b1 = [orc.circle_markers(1.5, 1.0, 0.3, 48)], [orc.circle_markers(1.56, 0.97, 0.3, 48)]
+    ck = str(tmp_path / "moved.ifx")
+    with ifx.ImmerseFlow(inp, xf, yf, **kw) as a:
+        a.initializeData(); a.set_bodies(b0)
+        a.step(); a.step()
+        a.set_bodies(b1); a.iblank_update()
+        a.save_checkpoint(ck, 2, 2e-3)
+        a.step()
+        want = {k: a.get(k) for k in ("u", "v", "p", "uf", "vf")}
+    with ifx.ImmerseFlow(inp, xf, yf, **kw) as c:
+        c.initializeData(); c.set_bodies(b1)
+        c.load_checkpoint(ck)
+        c.step()
+        for k, w in want.items():
+            assert np.array_equal(c.get(k), w), k
 
 
 def test_checkpoint_rejects_a_different_grid(tmp_path):
