@@ -421,6 +421,10 @@ extern "C" int ifx_create(const ifx_input* in, const double* xf, const double* y
   if (cudaMalloc(&s->celltype, s->field_elems) != cudaSuccess) { s->err = "cudaMalloc celltype"; return bail(IFX_ERR_CUDA); }
   launch_fill_u8(s->celltype, s->field_elems, IFX_FLUID, s->stream);
   s->launches++;
+  if (opt.compat == IFX_COMPAT_FULL) {
+    if (cudaMalloc(&s->facemask, s->field_elems) != cudaSuccess) { s->err = "cudaMalloc facemask"; return bail(IFX_ERR_CUDA); }
+    cudaMemsetAsync(s->facemask, 0, s->field_elems, s->stream);
+  }
   if (cudaMalloc(&s->ctl, sizeof(LoopCtl)) != cudaSuccess || cudaMallocHost(&s->h_ctl, sizeof(LoopCtl)) != cudaSuccess ||
       cudaMallocHost(&s->h_counters, sizeof(int) * 4) != cudaSuccess ||
       cudaMalloc(&s->red_out, sizeof(double) * 4) != cudaSuccess) {
@@ -457,6 +461,7 @@ extern "C" int ifx_destroy(ifx_solver* s) {
     for (double* q : a) if (q) cudaFree(q);
   }
   if (s->celltype) cudaFree(s->celltype);
+  if (s->facemask) cudaFree(s->facemask);
   if (s->ctl) cudaFree(s->ctl);
   if (s->h_ctl) cudaFreeHost(s->h_ctl);
   if (s->h_counters) cudaFreeHost(s->h_counters);
@@ -506,6 +511,7 @@ extern "C" int ifx_initialize(ifx_solver* s) {
   s->faces_valid = false;
   s->state_bc_fresh = false;
   s->bodies_dirty = s->nbodies > 0;      // the cell types were just reset to all-fluid
+  s->facemask_valid = false;
   s->has_gc = false;
   s->gc.count = 0;
   s->mg_valid = false;               // multigrid hierarchy and line eliminations were built for the old cell types
@@ -832,6 +838,17 @@ int ifx::run_ad_loop(ifx_solver* s, ifx_step_stats* st, bool full) {
 // ------------------------------------------------------------------------------------------------
 // Poisson — ImmerseFlow::PPESolver(), PPESolver.cu:137-205
 // ------------------------------------------------------------------------------------------------
+// face masks of the owned rows from the current cell types (the halo rows' types are classified locally, so the
+// first / last owned row of a slab sees its true neighbours)
+int ifx::ensure_facemask(ifx_solver* s) {
+  if (s->facemask_valid) return IFX_OK;
+  if (!s->facemask) return fail(s, IFX_ERR_STATE, "face masks exist in IFX_COMPAT_FULL only");
+  s->launches++;
+  IFX_CUDA(s, launch_build_facemask(s->L, s->celltype, s->facemask, 1, s->L.nyl - 1, s->stream));
+  s->facemask_valid = true;
+  return IFX_OK;
+}
+
 int ifx::enqueue_ppe_sweep(ifx_solver* s, PpeSweepArgs& a, dim3 grid, bool laplace_ref, bool write_res) {
   s->launches++;
   IFX_CUDA(s, ifx::launch_ppe_sweep_v4(a, grid, s->stream, laplace_ref, write_res));
@@ -870,7 +887,8 @@ int ifx::run_ppe_loop(ifx_solver* s, ifx_step_stats* st, bool laplace_ref) {
   if (itermax > 0) {
     PpeSweepArgs pa{};
     pa.L = L; pa.M = s->M;
-    pa.rhs = s->rhs; pa.celltype = s->celltype;
+    if (!laplace_ref && (rc = ensure_facemask(s)) != IFX_OK) return rc;
+    pa.rhs = s->rhs; pa.facemask = s->facemask;
     pa.res = s->res_a; pa.partials = s->partials; pa.ctl = s->ctl;
     pa.rows_per_cta = ry;
     pa.rc.itermax = itermax; pa.rc.tol = s->opt.ppe_tol; pa.rc.use_second = 0;

@@ -248,6 +248,7 @@ extern "C" int ifx_iblank_update(ifx_solver* s, ifx_step_stats* st) {
                                              "use fewer ranks for this grid");
   }
   s->bodies_dirty = false;
+  s->facemask_valid = false;       // the open faces of the Poisson operator moved with the bodies
   s->mg_valid = false;             // so did the open faces the coarse-level conductances are made of
   s->line_factor_valid = false;    // and the matrices of the line relaxation
   s->faces_valid = false;          // closed faces moved with the bodies

@@ -144,7 +144,8 @@ int ifx::run_ppe_multigrid(ifx_solver* s, ifx_step_stats* st) {
   if (itermax > 0) {
     PpeSweepArgs pa{};
     pa.L = L; pa.M = s->M;
-    pa.rhs = s->rhs; pa.celltype = s->celltype;
+    if ((rc = ensure_facemask(s)) != IFX_OK) return rc;
+    pa.rhs = s->rhs; pa.facemask = s->facemask;
     pa.res = s->res_a; pa.partials = s->partials; pa.ctl = s->ctl;
     pa.rows_per_cta = ry;
     pa.rc.itermax = itermax; pa.rc.tol = s->opt.ppe_tol; pa.rc.use_second = 0;
@@ -257,7 +258,8 @@ int ifx::run_ppe_lines(ifx_solver* s, ifx_step_stats* st) {
   if (itermax > 0) {
     PpeSweepArgs pa{};
     pa.L = L; pa.M = s->M;
-    pa.rhs = s->rhs; pa.celltype = s->celltype;
+    if ((rc = ensure_facemask(s)) != IFX_OK) return rc;
+    pa.rhs = s->rhs; pa.facemask = s->facemask;
     pa.res = s->res_a; pa.partials = s->partials; pa.ctl = s->ctl;
     pa.rows_per_cta = ry;
     pa.rc.itermax = itermax; pa.rc.tol = s->opt.ppe_tol; pa.rc.use_second = 0;

@@ -39,6 +39,8 @@ struct ifx_solver {
   int cur_uv = 0, cur_p = 0;
   double *sx = nullptr, *sy = nullptr, *rhs = nullptr, *uf = nullptr, *vf = nullptr;
   uint8_t* celltype = nullptr;
+  uint8_t* facemask = nullptr;       // open faces of the general Poisson operator, derived from the cell types (FULL mode)
+  bool facemask_valid = false;
   bool faces_valid = false;          // uf/vf hold projected face velocities (FULL mode)
 
   // reduction scratch
@@ -121,6 +123,7 @@ void fill_bc(const ifx_solver* s, double* two_u, double* two_v);
 int run_ad_loop(ifx_solver* s, ifx_step_stats* st, bool full);
 int run_ppe_loop(ifx_solver* s, ifx_step_stats* st, bool laplace_ref);
 int enqueue_ppe_sweep(ifx_solver* s, PpeSweepArgs& a, dim3 grid, bool laplace_ref, bool write_res);   // counts the launch
+int ensure_facemask(ifx_solver* s);     // (re)derives the face masks after the cell types changed
 int run_ppe_multigrid(ifx_solver* s, ifx_step_stats* st);      // capi_mg.cu
 int run_ppe_lines(ifx_solver* s, ifx_step_stats* st);
 int full_refresh_velocity_bc(ifx_solver* s, int buf);
