@@ -214,14 +214,14 @@ double ifx::rounding_band(const ifx_solver* s, size_t nblocks, int rows_per_cta)
 // slabs: halo context of a launch, generic halo exchange, waits
 // ------------------------------------------------------------------------------------------------
 static XchgSync* peer_sync(ifx_solver* s, int r) {
-  const size_t off = (6 * s->peer_field_elems[r] * sizeof(double) + 255) / 256 * 256;
+  const size_t off = ((size_t)s->nseg_fields * s->peer_field_elems[r] * sizeof(double) + 255) / 256 * 256;
   return reinterpret_cast<XchgSync*>(reinterpret_cast<char*>(s->peer_seg[r]) + off);
 }
 static double* peer_field(ifx_solver* s, int r, int field_index) {
   return reinterpret_cast<double*>(s->peer_seg[r]) + (size_t)field_index * s->peer_field_elems[r];
 }
 
-// field_index: 0,1 = u[0],u[1]; 2,3 = v[0],v[1]; 4,5 = p[0],p[1]
+// field_index: 0,1 = u[0],u[1]; 2,3 = v[0],v[1]; 4,5,(6) = p[0],p[1],(p[2])
 void ifx::make_halo_ctx(ifx_solver* s, int group, int nfields, const int* out_field_index, HaloCtx* hx) {
   std::memset(hx, 0, sizeof(*hx));
   hx->nranks = s->connected ? s->opt.nranks : 1;
@@ -390,14 +390,18 @@ extern "C" int ifx_create(const ifx_input* in, const double* xf, const double* y
     s->err = "bad rank / nranks (1..8 slabs)";
     return bail(IFX_ERR_INVALID);
   }
-  // exchange segment: the six ping-pong fields + the synchronisation area, one allocation (see common.cuh)
-  s->sync_off = (6 * s->field_elems * sizeof(double) + 255) / 256 * 256;
+  // exchange segment: the ping-pong fields + the synchronisation area, one allocation (see common.cuh).  A slab run
+  // keeps a third pressure buffer: its stop decision lags one sweep behind (no cross-GPU wait per sweep), so the
+  // converged iterate must survive two more sweeps (run_ppe_loop).
+  s->np = opt.nranks > 1 ? 3 : 2;
+  s->nseg_fields = 4 + s->np;
+  s->sync_off = ((size_t)s->nseg_fields * s->field_elems * sizeof(double) + 255) / 256 * 256;
   s->seg_bytes = s->sync_off + sizeof(XchgSync);
   if (cudaMalloc(&s->seg, s->seg_bytes) != cudaSuccess) { s->err = "cudaMalloc exchange segment"; return bail(IFX_ERR_CUDA); }
   cudaMemsetAsync(s->seg, 0, s->seg_bytes, s->stream);
   s->u[0] = s->seg; s->u[1] = s->seg + s->field_elems;
   s->v[0] = s->seg + 2 * s->field_elems; s->v[1] = s->seg + 3 * s->field_elems;
-  s->p[0] = s->seg + 4 * s->field_elems; s->p[1] = s->seg + 5 * s->field_elems;
+  for (int b = 0; b < s->np; b++) s->p[b] = s->seg + (size_t)(4 + b) * s->field_elems;
   s->sync = reinterpret_cast<XchgSync*>(reinterpret_cast<char*>(s->seg) + s->sync_off);
   s->peer_seg[opt.rank] = s->seg;
   s->peer_field_elems[opt.rank] = s->field_elems;
@@ -497,9 +501,9 @@ extern "C" int ifx_initialize(ifx_solver* s) {
   if (!s) return IFX_ERR_INVALID;
   IFX_CUDA(s, cudaSetDevice(s->device));
   const Layout& L = s->L;
-  for (int b = 0; b < 2; b++) {   // both ping-pong partners start from the same field
+  for (int b = 0; b < s->np; b++) {   // all ping-pong partners start from the same field
     s->launches++;
-    IFX_CUDA(s, launch_init_vortex(L, s->M.xc, s->M.yc, s->u[b], s->v[b], s->p[b], s->stream));
+    IFX_CUDA(s, launch_init_vortex(L, s->M.xc, s->M.yc, s->u[b & 1], s->v[b & 1], s->p[b], s->stream));
   }
   s->cur_uv = 0; s->cur_p = 0;
   s->launches++;
@@ -583,9 +587,11 @@ static int set_field_impl(ifx_solver* s, ifx_field f, const double* host, size_t
   }
   if (f == IFX_FIELD_U || f == IFX_FIELD_V || f == IFX_FIELD_P) {
     // keep the ping-pong partner's ghost ring consistent (a freshly set state has no history)
-    double* other = (f == IFX_FIELD_U) ? s->u[s->cur_uv ^ 1] : (f == IFX_FIELD_V) ? s->v[s->cur_uv ^ 1] : s->p[s->cur_p ^ 1];
-    s->launches++;
-    IFX_CUDA(s, launch_copy_ring(L, v.dev, other, nullptr, nullptr, s->stream));
+    for (int k = 1; k < (f == IFX_FIELD_P ? s->np : 2); k++) {
+      double* other = (f == IFX_FIELD_U) ? s->u[s->cur_uv ^ 1] : (f == IFX_FIELD_V) ? s->v[s->cur_uv ^ 1] : s->p[(s->cur_p + k) % s->np];
+      s->launches++;
+      IFX_CUDA(s, launch_copy_ring(L, v.dev, other, nullptr, nullptr, s->stream));
+    }
     if (f != IFX_FIELD_P) { s->faces_valid = false; s->state_bc_fresh = false; }
   }
   if (f == IFX_FIELD_UF || f == IFX_FIELD_VF) s->faces_valid = true;
@@ -750,6 +756,14 @@ int ifx::run_ad_loop(ifx_solver* s, ifx_step_stats* st, bool full) {
   ja.rc.decide = exact ? 0 : 1;
   ja.rc.certify = (exact || slabs) ? 0 : 1;     // slabs: the global sum is taken as is (+-1 at the rounding edge)
   ja.rc.band = rounding_band(s, nblocks, ry);
+  // Slabs: the stop decision LAGS one sweep (every launch posts its partial sums and decides on its predecessor's, a
+  // flush kernel decides on the last launch of a batch).  Sweep m+1 then runs although iteration m converged; it
+  // writes the buffer of iterate m-1, so iterate m — the result — is intact.  No rank waits for another rank's
+  // residual on its critical path any more (76 global lock steps per step in round 1, profiles/r1_scaling.md).
+  // Full mode only: the extra sweep also rewrites the ghost ring of ITS input buffer — the result's — which the full
+  // step refreshes anyway, whereas the reference-compatible step reads that ring as the reference left it (App. A Q5).
+  const bool lag = slabs && full;
+  bool lag_first = true;
   unsigned seq_before = s->seq[0];
   // ghost cells on slabs: sweep -> ghost-cell kernel (reads the neighbours' previous iterate) -> push kernel, which
   // re-delivers the boundary rows (now with their ghost cells) and only then publishes the sweep's sequence number
@@ -761,6 +775,8 @@ int ifx::run_ad_loop(ifx_solver* s, ifx_step_stats* st, bool full) {
     ja.uC = s->u[src]; ja.vC = s->v[src];
     ja.uT = s->u[src ^ 1]; ja.vT = s->v[src ^ 1];
     ja.rc.eval_iter = m;
+    ja.rc.lag = lag ? 1 : 0; ja.rc.lag_first = lag_first ? 1 : 0;
+    lag_first = false;
     const int fo[2] = {src ^ 1, 2 + (src ^ 1)};
     make_halo_ctx(s, 0, 2, fo, &ja.hx);
     ja.hx.defer = defer ? 1 : 0;
@@ -786,6 +802,11 @@ int ifx::run_ad_loop(ifx_solver* s, ifx_step_stats* st, bool full) {
         if ((rc = halo_push(s, 0, 2, fo, tw_ad, ja.hx.seq, s->ctl, m)) != IFX_OK) return rc;
       }
       if (exact && (rc = exact_decide(s, ja.rc, true)) != IFX_OK) return rc;
+    }
+    if (lag) {      // the batch's last sweep has no successor to decide on it
+      s->launches++;
+      IFX_CUDA(s, launch_lag_flush(s->ctl, ja.rc, ja.hx, s->stream));
+      lag_first = true;
     }
     if ((rc = fetch_ctl(s)) != IFX_OK) return rc;
     if (s->h_ctl->done && s->h_ctl->ambiguous && !slabs) {
@@ -875,7 +896,10 @@ int ifx::run_ppe_loop(ifx_solver* s, ifx_step_stats* st, bool laplace_ref) {
     // set_pressure_BC (PPESolver.cu:164); the ring is then carried through every sweep (:21)
     s->launches += 2;
     IFX_CUDA(s, launch_set_pressure_bc_ref(L, s->p[base], nullptr, s->stream));
-    IFX_CUDA(s, launch_copy_ring(L, s->p[base], s->p[base ^ 1], nullptr, nullptr, s->stream));
+    for (int k = 1; k < s->np; k++) {
+      if (k > 1) s->launches++;
+      IFX_CUDA(s, launch_copy_ring(L, s->p[base], s->p[(base + k) % s->np], nullptr, nullptr, s->stream));
+    }
   }
   IFX_CUDA(s, cudaMemsetAsync(s->ctl, 0, sizeof(LoopCtl), s->stream));
   int K = 0, fallbacks = 0;
@@ -902,17 +926,28 @@ int ifx::run_ppe_loop(ifx_solver* s, ifx_step_stats* st, bool laplace_ref) {
     const bool sor = !laplace_ref && s->opt.ppe_solver == 3;
     pa.sor = sor ? 1 : 0; pa.sor_omega = s->opt.ppe_omega;
     const int decide = pa.rc.decide;
+    // Slabs, Jacobi: lagged stop decision (see run_ad_loop).  Sweep m evaluates the residual of iterate m-1; the
+    // decision falls at the end of sweep m+1, which has written iterate m+1 by then — so the buffers rotate three
+    // ways and iterate m-1, the result, is still intact.  Red-black SOR keeps the lock step (its iterate lives in one
+    // buffer; a late decision would find it overwritten).
+    const int np = s->np;
+    const bool lag = slabs && !sor;
+    bool lag_first = true;
+    const int partner = (base + 1) % np;      // SOR: the other buffer of the pair
     auto set_sweep = [&](int m) {     // sweep m: iterate m-1 -> iterate m, evaluates residual(iterate m-1)
-      const int src = sor ? base : (base + m - 1) & 1;
-      pa.pC = s->p[src]; pa.pT = s->p[src ^ 1];
+      const int src = sor ? base : (base + m - 1) % np;
+      const int dst = sor ? partner : (base + m) % np;
+      pa.pC = s->p[src]; pa.pT = s->p[dst];
       pa.rc.eval_iter = m - 1;
       pa.rc.decide = decide;
+      pa.rc.lag = lag ? 1 : 0; pa.rc.lag_first = lag_first ? 1 : 0;
+      lag_first = false;
       pa.sor_colour = 0;
-      const int fo[1] = {4 + (src ^ 1)};
+      const int fo[1] = {4 + dst};
       make_halo_ctx(s, 1, 1, fo, &pa.hx);
     };
     auto set_black = [&]() {          // second half of a SOR iteration: no residual bookkeeping
-      pa.pC = s->p[base ^ 1]; pa.pT = s->p[base];
+      pa.pC = s->p[partner]; pa.pT = s->p[base];
       pa.rc.eval_iter = 0; pa.rc.decide = 0;
       pa.sor_colour = 1;
       const int fo[1] = {4 + base};
@@ -930,6 +965,11 @@ int ifx::run_ppe_loop(ifx_solver* s, ifx_step_stats* st, bool laplace_ref) {
           set_black();
           if ((rc = enqueue_ppe_sweep(s, pa, grid, laplace_ref, false)) != IFX_OK) return rc;
         }
+      }
+      if (lag) {
+        s->launches++;
+        IFX_CUDA(s, launch_lag_flush(s->ctl, pa.rc, pa.hx, s->stream));
+        lag_first = true;
       }
       if ((rc = fetch_ctl(s)) != IFX_OK) return rc;
       if (s->h_ctl->done && s->h_ctl->ambiguous && !slabs) {
@@ -953,7 +993,7 @@ int ifx::run_ppe_loop(ifx_solver* s, ifx_step_stats* st, bool laplace_ref) {
       if (m >= itermax + 1) return fail(s, IFX_ERR_STATE, "Poisson loop ran past PPE_itermax without a decision");
     }
     K = s->h_ctl->iter;
-    s->cur_p = sor ? base : (base + K) & 1;
+    s->cur_p = sor ? base : (base + K) % np;
     if (slabs && (rc = halo_wait(s, 1, seq_before + (unsigned)(sor ? 2 * K : K), tw_ppe)) != IFX_OK) return rc;
   }
   if (laplace_ref) {   // PPESolver.cu:195

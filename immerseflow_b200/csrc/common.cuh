@@ -96,12 +96,14 @@ struct LoopCtl {
 #define IFX_MAX_RANKS 8
 #define IFX_MAX_TILES 1024
 #define IFX_SYNC_GROUPS 3          // 0: predictor sweeps (u, v), 1: Poisson sweeps (p), 2: everything else
-#define IFX_MAIL_SLOTS 4
+#define IFX_MAIL_SLOTS 8
+#define IFX_MAIL_VALS 4            // doubles per mailbox entry (two residual pairs: a launch may carry two sweeps)
+#define IFX_SEG_FIELDS_MAX 8       // fields an exchange segment may hold: u[2], v[2], p[3] (+1 spare)
 #define IFX_GC_REACH 4             // rows beyond its slab a ghost-cell stencil may read from the neighbour's memory
 
 struct XchgSync {
   unsigned flags[IFX_SYNC_GROUPS][2][IFX_MAX_TILES];      // [group][0: written by lower nbr, 1: by upper][tile]
-  double mail[IFX_MAIL_SLOTS][IFX_MAX_RANKS][2];          // per-rank residual partials of one sweep
+  double mail[IFX_MAIL_SLOTS][IFX_MAX_RANKS][IFX_MAIL_VALS];   // per-rank residual partials of one launch
   unsigned mail_seq[IFX_MAIL_SLOTS][IFX_MAX_RANKS];
 };
 

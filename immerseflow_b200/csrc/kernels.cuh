@@ -16,6 +16,9 @@ struct ReduceCfg {
   int use_second;   // stop test on res0 + res1 (predictor: uRes + vRes, ADSolver.cu:315)
   int test_abs;     // PPE: test res1 (= sum |r|) instead of the signed res0
   int certify;      // flag decisions that fall inside the rounding band instead of taking them
+  int lag;          // slabs: post this launch's partials, decide on the PREVIOUS launch's (no cross-GPU wait on the
+                    // critical path); the loop's last launch is decided by a flush kernel (launch_lag_flush)
+  int lag_first;    // lag: first launch of the loop or after a flush — nothing to decide yet
   double tol;
   double band;      // relative half-width of the rounding band (times the abs-sum)
 };
@@ -74,23 +77,51 @@ struct PpeSweepArgs {
 // global residual over the slabs: every rank posts its partial into every rank's mailbox (NVLink P2P stores),
 // then adds all of them in rank order — same operands, same order, same stop decision everywhere.  One thread of
 // one CTA per launch runs this: kept out of line so that it does not set the register count of the sweep kernels.
-static __device__ __noinline__ void slab_combine_residual(const HaloCtx& hx, double& a, double& b) {
-  const unsigned slot = hx.mseq & (IFX_MAIL_SLOTS - 1);
+// Two halves: POST (my partial of launch `tag` into everybody's mailbox) and COLLECT (add the partials of launch
+// `tag`, waiting for stragglers).  A lock-step launch does both for its own tag; a LAGGED launch posts its own and
+// collects the previous launch's, which arrived a whole sweep ago — the ranks then drift by up to one launch instead
+// of meeting 76 times per step (profiles/r1_scaling.md).
+static __device__ __noinline__ void slab_post_partial(const HaloCtx& hx, unsigned tag, double a, double b) {
+  const unsigned slot = tag & (IFX_MAIL_SLOTS - 1);
   const unsigned me = (unsigned)hx.rank;
   for (int r = 0; r < hx.nranks; ++r) {
-    double* m = hx.mail[r] + ((size_t)slot * IFX_MAX_RANKS + me) * 2;
+    double* m = hx.mail[r] + ((size_t)slot * IFX_MAX_RANKS + me) * IFX_MAIL_VALS;
     m[0] = a; m[1] = b;
   }
   __threadfence_system();
-  for (int r = 0; r < hx.nranks; ++r) st_release_sys(hx.mail_seq[r] + slot * IFX_MAX_RANKS + me, hx.mseq);
+  for (int r = 0; r < hx.nranks; ++r) st_release_sys(hx.mail_seq[r] + slot * IFX_MAX_RANKS + me, tag);
+}
+static __device__ __noinline__ void slab_collect_partials(const HaloCtx& hx, unsigned tag, double& a, double& b) {
+  const unsigned slot = tag & (IFX_MAIL_SLOTS - 1);
+  const unsigned me = (unsigned)hx.rank;
   double ga = 0.0, gb = 0.0;
   for (int r = 0; r < hx.nranks; ++r) {
     const unsigned* q = hx.mail_seq[me] + slot * IFX_MAX_RANKS + r;
-    while (ld_acquire_sys(q) != hx.mseq) { __nanosleep(64); }
-    const volatile double* m = hx.mail[me] + ((size_t)slot * IFX_MAX_RANKS + r) * 2;
+    while (ld_acquire_sys(q) != tag) { __nanosleep(64); }
+    const volatile double* m = hx.mail[me] + ((size_t)slot * IFX_MAX_RANKS + r) * IFX_MAIL_VALS;
     ga += m[0]; gb += m[1];
   }
   a = ga; b = gb;
+}
+
+// the stop decision on a pair of global residual sums (one thread)
+__device__ __forceinline__ void decide_on_residual(LoopCtl* ctl, const ReduceCfg& rc, int eval_iter, double a, double b) {
+  ctl->res0 = a;
+  ctl->res1 = b;
+  if (eval_iter < 1) return;
+  if (eval_iter <= 64) { ctl->hist[2 * (eval_iter - 1)] = a; ctl->hist[2 * (eval_iter - 1) + 1] = b; }
+  if (!rc.decide) return;
+  ctl->iter = eval_iter;
+  const double S = rc.use_second ? a + b : (rc.test_abs ? b : a);
+  const double A = rc.use_second ? S : b;           // sum of magnitudes
+  const bool at_max = eval_iter >= rc.itermax;
+  if (rc.certify && !at_max && fabs(S - rc.tol) <= rc.band * A) {
+    ctl->ambiguous = 1;
+    ctl->done = 1;
+  } else if (!(S > rc.tol) || at_max) {
+    ctl->hit_max = (S > rc.tol) ? 1 : 0;
+    ctl->done = 1;
+  }
 }
 
 template <int THREADS>
@@ -132,26 +163,20 @@ __device__ __forceinline__ void block_reduce_and_decide(double r0, double r1, do
     a = sh[0][0]; b = sh[1][0];
 #pragma unroll
     for (int w = 1; w < NW; ++w) { a += sh[0][w]; b += sh[1][w]; }
-    if (hx && hx->nranks > 1) slab_combine_residual(*hx, a, b);
     ctl->ticket = 0;
-    ctl->res0 = a;
-    ctl->res1 = b;
-    if (rc.eval_iter >= 1) {
-      if (rc.eval_iter <= 64) { ctl->hist[2 * (rc.eval_iter - 1)] = a; ctl->hist[2 * (rc.eval_iter - 1) + 1] = b; }
-      if (rc.decide) {
-        ctl->iter = rc.eval_iter;
-        const double S = rc.use_second ? a + b : (rc.test_abs ? b : a);
-        const double A = rc.use_second ? S : b;           // sum of magnitudes
-        const bool at_max = rc.eval_iter >= rc.itermax;
-        if (rc.certify && !at_max && fabs(S - rc.tol) <= rc.band * A) {
-          ctl->ambiguous = 1;
-          ctl->done = 1;
-        } else if (!(S > rc.tol) || at_max) {
-          ctl->hit_max = (S > rc.tol) ? 1 : 0;
-          ctl->done = 1;
-        }
+    int eval_iter = rc.eval_iter;
+    bool decide = true;
+    if (hx && hx->nranks > 1) {
+      slab_post_partial(*hx, hx->mseq, a, b);
+      if (rc.lag) {                        // the previous launch's sums (every rank posted them a sweep ago)
+        eval_iter -= 1;
+        decide = !rc.lag_first;
+        if (decide) slab_collect_partials(*hx, hx->mseq - 1, a, b);
+      } else {
+        slab_collect_partials(*hx, hx->mseq, a, b);
       }
     }
+    if (decide) decide_on_residual(ctl, rc, eval_iter, a, b);
     __threadfence();
   }
 }
@@ -225,6 +250,8 @@ struct HaloPushArgs {
 };
 cudaError_t launch_halo_push(const HaloPushArgs& a, cudaStream_t st);
 cudaError_t launch_halo_wait(const unsigned* wait_lo, const unsigned* wait_hi, int ntiles, unsigned need, cudaStream_t st);
+// lagged stop decision: decide on the LAST launch of a batch (rc, hx: that launch's), unless the loop is already done
+cudaError_t launch_lag_flush(LoopCtl* ctl, const ReduceCfg& rc, const HaloCtx& hx, cudaStream_t st);
 // kernels_reduce.cu — the reference's summation order (preSim.cu:12-50, 376-441)
 cudaError_t launch_reduce6(const double* in, size_t n, double* partial, double* out, cudaStream_t st,
                            bool abs_values = false);

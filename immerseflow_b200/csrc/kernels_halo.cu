@@ -39,6 +39,21 @@ static __global__ void k_halo_wait(const unsigned* wait_lo, const unsigned* wait
   __threadfence_system();
 }
 
+// Lagged stop decision (ReduceCfg.lag): every sweep decides on its predecessor's residual; the last sweep of a batch
+// has no successor, so this one-thread kernel collects its partials and decides.  Every rank runs it at the same
+// point of the same launch sequence and adds the same operands in the same order: same decision everywhere.
+static __global__ void k_lag_flush(LoopCtl* ctl, ReduceCfg rc, HaloCtx hx) {
+  if (threadIdx.x != 0 || ctl->done) return;
+  double a = 0.0, b = 0.0;
+  slab_collect_partials(hx, hx.mseq, a, b);
+  decide_on_residual(ctl, rc, rc.eval_iter, a, b);
+  __threadfence();
+}
+cudaError_t launch_lag_flush(LoopCtl* ctl, const ReduceCfg& rc, const HaloCtx& hx, cudaStream_t st) {
+  k_lag_flush<<<1, 32, 0, st>>>(ctl, rc, hx);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_halo_push(const HaloPushArgs& a, cudaStream_t st) {
   k_halo_push<<<a.ntiles, 256, 0, st>>>(a);
   return cudaGetLastError();

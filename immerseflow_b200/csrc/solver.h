@@ -35,7 +35,9 @@ struct ifx_solver {
   size_t field_elems = 0;            // doubles per padded field allocation
   double* u[2] = {nullptr, nullptr};
   double* v[2] = {nullptr, nullptr};
-  double* p[2] = {nullptr, nullptr};
+  double* p[3] = {nullptr, nullptr, nullptr};   // slab runs rotate THREE pressure buffers (lagged stop decision, capi.cu)
+  int np = 2;                        // pressure buffers in use
+  int nseg_fields = 6;               // fields in the exchange segment: u[2], v[2], p[np]
   int cur_uv = 0, cur_p = 0;
   double *sx = nullptr, *sy = nullptr, *rhs = nullptr, *uf = nullptr, *vf = nullptr;
   uint8_t* celltype = nullptr;
