@@ -40,8 +40,14 @@ def parse_args():
     ap.add_argument("--ppe-sweeps", type=int, default=50, help="PPE_itermax for the bench step (bounded Poisson solve)")
     ap.add_argument("--dt", type=float, default=1e-3)
     ap.add_argument("--Re", type=float, default=150.0)
-    ap.add_argument("--cpu-sample-rows", type=int, default=192, help="rows of the workload the CPU baseline runs on")
+    ap.add_argument("--cpu-sample-rows", type=int, default=2048,
+                    help="rows of the workload the CPU arm runs on (a row slab through the first lattice row of bodies; >= 1/8 of the grid)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity-check", action="store_true",
+                    help="skip the bit-for-bit check of the timed workload's first step against the CPU oracle (rank 0) and, on "
+                         "more than one GPU, of a slab run against a single-GPU run")
+    ap.add_argument("--no-ref-cuda", action="store_true",
+                    help="skip timing the reference's own CUDA build (oracle/_ref/immerseFlow_ref) on this GPU")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-handles", type=int, default=3,
                     help="simulations in flight in the end-to-end measurement: 3 = one uploading its next state, one stepping, "
@@ -198,30 +204,63 @@ def bodies_at(nb: int, step: int, dt: float):
 
 
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_arm(args, rows: int, steps: int, warmup: int):
-    """The reference has no CPU path; its reported CPU baseline is the OpenMP transcription of its loops
-    (oracle/, `kind: port`), run with every host thread on a bounded row-slab of the same workload (same grid
-    width, same parameters, same iteration caps, `rows` of the 16384 rows)."""
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import _oracle as orc
-    import immerseflow_b200 as ifx
-    ncx, ncy = args.nx, min(rows, args.ny)
-    xf = ifx.uniform_faces(ncx, 1.0)
+PARITY_MARGIN = 200     # rows.  One step moves information by at most 25 predictor iterations x 4 cells (a ghost cell's
+                        # closure reads nodes up to 4 cells away) + 50 Poisson sweeps x 1 cell + a few cells (faces, source
+                        # term, projection): < 200, so the oracle's artificial slab walls cannot reach further in
+
+
+def cpu_slab_rows(args, rows: int):
+    """Row slab [r0, r0 + ncy) (cell rows) of the workload the CPU arm runs on: through the first lattice row of bodies."""
+    ncy = min(rows, args.ny)
     r0 = 0
-    if args.bodies > 0 and args.mode == "full":      # the slab that cuts through the first lattice row of bodies
+    if args.bodies > 0 and args.mode == "full":
         cols = int(np.ceil(np.sqrt(args.bodies)))
         nrow = (args.bodies + cols - 1) // cols
         r0 = max(0, min(args.ny - ncy, int(0.5 / nrow * args.ny) - ncy // 2))
+    return r0, ncy
+
+
+def initial_pressure(nx: int, ny_global: int, row0: int, nrows: int) -> np.ndarray:
+    """The bench's smooth non-zero starting pressure on rows [row0, row0 + nrows) of the ghost-inclusive grid (the
+    reference starts from p == 0, which turns most quotients of the first sweeps into exact zeros — an arithmetic special
+    case).  A function of the GLOBAL cell index, so every slab of every decomposition (and the CPU arm) sees the same field."""
+    jj, ii = np.divmod(np.arange(nrows * nx, dtype=np.float64), float(nx))
+    jj += row0
+    return 50.0 + 40.0 * np.sin(ii * (6.283185307179586 / nx)) * np.cos(jj * (6.283185307179586 / ny_global))
+
+
+def host_threads() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def cpu_reference_arm(args, rows: int, steps: int, warmup: int, keep_first_step: bool = False, ic=None):
+    """The reference has no CPU path; its reported CPU baseline is the OpenMP transcription of its loops
+    (oracle/, `kind: port`), run with every host thread (set explicitly: torchrun exports OMP_NUM_THREADS=1) on a
+    bounded row slab of the same workload (same grid width, same parameters, same iteration caps, `rows` of the rows).
+    keep_first_step: also return the slab's u, v, p after the first step from the initial condition (parity check).
+    ic: the slab's rows of the initial u, v as the CUDA path holds them (its vortex kernel uses CUDA's exp / pow, glibc's
+    differ in the last bit: a parity check of the STEP needs the same input on both sides)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import _oracle as orc
+    import immerseflow_b200 as ifx
+    r0, ncy = cpu_slab_rows(args, rows)
+    ncx = args.nx
+    xf = ifx.uniform_faces(ncx, 1.0)
     yf = ifx.uniform_faces(args.ny, 1.0)[r0: r0 + ncy + 1]
+    orc.lib().orc_set_num_threads(host_threads())
     cores = orc.lib().orc_num_threads()
-    times, k_ad, k_ppe = [], 0, 0
+    times, k_ad, k_ppe, first = [], 0, 0, None
     if args.mode == "full":
         fs = orc.FullSolver(xf, yf, args.dt, args.Re, args.ad_itermax, args.ppe_sweeps, ppe_tol=0.0, ppe_abs=1)
         g = orc.Grid(xf, yf)
         u, v, p = orc.initial_condition(g)
+        if ic is not None:
+            u, v = ic["u"].reshape(-1), ic["v"].reshape(-1)
         fs.set("u", u); fs.set("v", v)
-        jj, ii = np.divmod(np.arange(g.nx * g.ny, dtype=np.float64), float(g.nx))
-        fs.set("p", 50.0 + 40.0 * np.sin(ii * (6.283185307179586 / g.nx)) * np.cos(jj * (6.283185307179586 / (args.ny + 2))))
+        fs.set("p", initial_pressure(g.nx, args.ny + 2, r0, g.ny))
         fs.update_ib()
         for it in range(warmup + steps):
             t0 = time.perf_counter()
@@ -233,10 +272,15 @@ def cpu_reference_arm(args, rows: int, steps: int, warmup: int):
             if it >= warmup:
                 times.append(time.perf_counter() - t0)
             k_ad, k_ppe = int(st[0]), int(st[3])
+            if it == 0 and keep_first_step:
+                first = {k: fs.get(k) for k in ("u", "v", "p")}
         fs.close()
     else:
         g = orc.Grid(xf, yf)
         u, v, p = orc.initial_condition(g)
+        if ic is not None:
+            u, v = ic["u"].reshape(-1), ic["v"].reshape(-1)
+        p = initial_pressure(g.nx, args.ny + 2, r0, g.ny)
         pr = orc.Predictor(g, u, v, args.dt, args.Re, args.ad_itermax)
         for it in range(warmup + steps):
             t0 = time.perf_counter()
@@ -244,11 +288,62 @@ def cpu_reference_arm(args, rows: int, steps: int, warmup: int):
             k_ppe, p, _ = orc.ppe_solve(g, p, args.ppe_sweeps)
             if it >= warmup:
                 times.append(time.perf_counter() - t0)
+            if it == 0 and keep_first_step:
+                first = {"u": pr.u.copy(), "v": pr.v.copy(), "p": p.copy()}
     cells = ncx * ncy
-    t = float(np.mean(times))
-    return {"value": cells / t / 1e6, "unit": METRIC, "cores": cores, "kind": "port",
-            "sample": f"{ncx}x{ncy}-cell row slab (rows {r0}..{r0 + ncy}) of the workload ({args.mode} step), {steps} step(s) "
-                      f"(K_AD={k_ad}, {k_ppe} Poisson sweeps), OpenMP x{cores}", "ms_per_step": t * 1e3}
+    t = float(np.mean(times)) if times else float("nan")
+    out = {"value": cells / t / 1e6, "unit": METRIC, "cores": cores, "kind": "port",
+           "sample": f"{ncx}x{ncy}-cell row slab (rows {r0}..{r0 + ncy} of {args.ny}, {100.0 * ncy / args.ny:.1f} % of the grid; throughput "
+                     f"per cell of the slab) of the workload ({args.mode} step), {steps} step(s) after {warmup} warm-up "
+                     f"(K_AD={k_ad}, {k_ppe} Poisson sweeps), OpenMP x{cores}", "ms_per_step": t * 1e3,
+           "sample_rows": [r0, r0 + ncy], "sample_fraction": ncy / args.ny}
+    if keep_first_step:
+        out["first_step"] = first
+        out["grid"] = (g.nx, g.ny)
+    return out
+
+
+def row_digests(field: np.ndarray, nx: int, rows) -> list:
+    """One 16-byte digest per row of a reference-layout field: what the ranks exchange instead of gigabytes."""
+    import hashlib
+    f = field.reshape(-1, nx)
+    return [hashlib.blake2b(np.ascontiguousarray(f[r, 1:-1]).tobytes(), digest_size=16).digest() for r in rows]
+
+
+def ref_cuda_baseline(args):
+    """The reference's OWN CUDA build (oracle/_ref/immerseFlow_ref: its unmodified translation units, file output
+    stubbed) timed on this GPU — north_star's second reported baseline.  Its time step is the predictor only
+    (src/main.cu:93-96 -> ADSolver.cu:268-395), all cells fluid.  Per-step time = difference of two runs (start-up,
+    allocation and grid I/O cancel).  Bounded: one run of 4 steps."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    try:
+        import ref_cuda_baseline as rcb
+        import shutil
+        if not os.path.exists(rcb.REF):
+            return {"unavailable": "oracle/_ref/immerseFlow_ref not built here (needs /root/reference at build time)"}
+        if args.nx > args.ny:
+            return {"unavailable": "the reference overruns its vf allocation for nx > ny (preSim.cu:153)"}
+        w = tempfile.mkdtemp(prefix="ifx_ref_")
+        try:
+            for d in ("src", "inputs", "results"):
+                os.makedirs(os.path.join(w, d))
+            rcb.write_grid(os.path.join(w, "inputs", "xgrid.dat2"), args.nx)
+            rcb.write_grid(os.path.join(w, "inputs", "ygrid.dat2"), args.ny)
+            nsteps = 4
+            ta, ia, ends = rcb.run(args.nx, args.ny, args.ad_itermax, args.dt, args.Re, nsteps, w)
+        finally:
+            shutil.rmtree(w, ignore_errors=True)
+        if len(ends) < 2:
+            return {"unavailable": "the reference did not report the end of two steps (converged before AD_itermax?)"}
+        per = (ends[-1] - ends[0]) / (len(ends) - 1)
+        return {"impl": "reference CUDA build (unmodified TUs of /root/reference/src, nvcc -arch=sm_100, file output stubbed)",
+                "work": "the reference's time step = predictor only (src/main.cu:93-96), no immersed body",
+                "ms_per_step": per * 1e3, "value": args.nx * args.ny / per / 1e6, "unit": METRIC,
+                "predictor_iterations_per_step": ia / nsteps, "wall_s": ta, "step_end_times_s": ends,
+                "method": "spacing of the reference's own `iter = <AD_itermax>` lines (end of every time step) on a line-buffered "
+                          "pipe: start-up, allocation and grid I/O are outside"}
+    except Exception as ex:       # noqa: BLE001 — reported, never fatal
+        return {"unavailable": f"{type(ex).__name__}: {ex}"[:300]}
 
 
 def measured_traffic(kernel: str, nx: int, ny: int):
@@ -262,6 +357,61 @@ def measured_traffic(kernel: str, nx: int, ny: int):
     except Exception:
         pass
     return None
+
+
+def slab_parity_check(ifx, slabs, dist, torch, rank, world, dev):
+    """world > 1: a 2048 x 2048 full-mode run with moving bodies that straddle the slab boundaries, slab-decomposed
+    over all ranks, against the same run on ONE GPU (rank 0): every owned row of u, v, p, bit for bit (row digests),
+    and the iteration counts.  What tests/test_gpu_slabs.py checks, inside the benchmark's own process group."""
+    ncx = ncy = 2048
+    dt, Re = 1e-3, 150.0
+    inp = ifx.make_input(ncx, ncy, dt, Re, AD_itermax=12, PPE_itermax=40)
+    xf, yf = ifx.uniform_faces(ncx, 1.0), ifx.uniform_faces(ncy, 1.0)
+    nsteps, nb = 2, 4
+    kw = dict(compat=ifx.IFX_COMPAT_FULL, ppe_abs_residual=1, sweeps_per_batch=16)
+
+    def run(h, lo_row):
+        h.initializeData()
+        h.set("p", initial_pressure(inp.nx, inp.ny, lo_row, h.field_size("p") // inp.nx))
+        return h
+
+    jb, je = slabs.partition_rows(inp.ny, world)[rank]
+    h = run(ifx.ImmerseFlow(inp, xf, yf, device=dev, rank=rank, nranks=world, j_begin=jb, j_end=je, **kw), jb - 1)
+    slabs.connect(h, dist)
+    counts = []
+    for it in range(nsteps):
+        b, vel = bodies_at(nb, 40 * it, dt)          # 40 steps' worth of motion per step: the cell types change
+        h.set_bodies(b, vel)
+        st = h.step()
+        counts.append((st.ad_iters, st.ppe_sweeps))
+    mine = {k: row_digests(h.get(k), inp.nx, range(1, je - jb + 1)) for k in ("u", "v", "p")}
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (counts, mine))
+    dist.barrier()
+    h.close()
+    out = None
+    if rank == 0:
+        r = run(ifx.ImmerseFlow(inp, xf, yf, device=dev, **kw), 0)
+        rc = []
+        for it in range(nsteps):
+            b, vel = bodies_at(nb, 40 * it, dt)
+            r.set_bodies(b, vel)
+            st = r.step()
+            rc.append((st.ad_iters, st.ppe_sweeps))
+        ref = {k: row_digests(r.get(k), inp.nx, range(1, inp.ny - 1)) for k in ("u", "v", "p")}
+        ghost = int(r.lib.ifx_ghost_cell_count(r._h))
+        r.close()
+        bad = 0
+        for q, (cq, dq) in enumerate(gathered):
+            qb, qe = slabs.partition_rows(inp.ny, world)[q]
+            for k in ("u", "v", "p"):
+                bad += sum(1 for a_, b_ in zip(dq[k], ref[k][qb - 1:qe - 1]) if a_ != b_)
+            if cq != rc:
+                bad += 1
+        out = {"bit_exact": bad == 0, "grid": [ncx, ncy], "steps": nsteps, "ranks": world, "bodies": nb, "ghost_cells": ghost,
+               "iteration_counts": rc, "mismatching_rows": bad,
+               "what": "u, v, p of every owned row (digests) and the iteration counts of the slab run == the single-GPU run"}
+    return out
 
 
 def main():
@@ -282,17 +432,18 @@ def main():
                   8 * 8.0 * (args.nx + 2) * (args.ny + 2) / 1e9,
                   "inputs larger than L2, no flush needed" if 8 * 8.0 * (args.nx + 2) * (args.ny + 2) > 4 * 126e6
                   else "NOT larger than L2: an HBM fraction measured on this grid is an L2 figure"),
-              "decomposition": f"{world} row slab(s), halo rows by in-kernel NVLink P2P stores, residual by P2P mailboxes"}
+              "decomposition": f"{world} row slab(s), halo rows by in-kernel NVLink P2P stores, residual sums by P2P mailboxes "
+                               f"(stop decision one sweep behind)"}
 
     if args.impl == "reference":
         if rank != 0:
             return
-        steps = max(1, min(args.steps, 3))
-        cb = cpu_reference_arm(args, max(args.cpu_sample_rows, 768), steps, min(args.warmup, 1))
+        steps, warmup = max(1, args.steps), max(0, args.warmup)
+        cb = cpu_reference_arm(args, args.cpu_sample_rows, steps, warmup)
         line = {"metric": METRIC, "value": cb["value"], "unit": METRIC, "n_gpus": args.gpus, "steps": steps,
-                "warmup": min(args.warmup, 1), "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "strong",
+                "warmup": warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference", "config": config,
-                "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "sample_fraction")},
                 "e2e": {"value": cb["value"], "unit": METRIC, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return
@@ -300,7 +451,9 @@ def main():
     import torch
     import immerseflow_b200 as ifx
 
+    dist = None
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")          # keeps NCCL's version banner off stdout (one JSON line)
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl")
@@ -316,6 +469,10 @@ def main():
         jb, je = slabs.partition_rows(inp.ny, args.emulate_slab_of)[0]
     full = args.mode == "full"
 
+    slab_parity = None
+    if world > 1 and not args.no_parity_check:
+        slab_parity = slab_parity_check(ifx, slabs, dist, torch, rank, world, dev)
+
     p0 = []
 
     def make_solver(zero_copy_control=0):
@@ -324,15 +481,8 @@ def main():
                             j_begin=jb, j_end=je, compat=ifx.IFX_COMPAT_FULL if full else ifx.IFX_COMPAT_REFERENCE,
                             ppe_abs_residual=1 if full else 0, zero_copy_control=zero_copy_control)
         h.initializeData()
-        # The reference starts the Poisson solve from p == 0 (preSim.cu:67), which makes most quotients exact zeros for
-        # the first sweeps — an arithmetic special case.  The bench uses a smooth non-zero pressure field so that every
-        # fp64 division takes the normal-operand path a converging solve sees.
         if not p0:                         # computed once, shared by the handles of the end-to-end pipeline
-            n_p = h.field_size("p")
-            jj, ii = np.divmod(np.arange(n_p, dtype=np.float64), float(inp.nx))
-            jj += jb - 1
-            p0.append(50.0 + 40.0 * np.sin(ii * (6.283185307179586 / inp.nx)) * np.cos(jj * (6.283185307179586 / inp.ny)))
-            del jj, ii
+            p0.append(initial_pressure(inp.nx, inp.ny, jb - 1, h.field_size("p") // inp.nx))
         h.set("p", p0[0])
         if world > 1:
             slabs.connect(h, dist)
@@ -360,7 +510,64 @@ def main():
         b = h.PPESolver()
         return a, b
 
-    for _ in range(args.warmup):
+    # ---- parity of THIS workload, before anything is timed: the first step from the initial condition, the rows well
+    # inside the CPU arm's row slab (the oracle runs that slab with walls where the grid goes on), bit for bit
+    parity_gpu = None
+    do_parity = not args.no_parity_check and not args.emulate_slab_of
+    warm_done = 0
+    if do_parity:
+        r0, nrows_cpu = cpu_slab_rows(args, args.cpu_sample_rows)
+        lo, hi = r0 + PARITY_MARGIN + 1, r0 + nrows_cpu - PARITY_MARGIN + 1       # ghost-inclusive global rows [lo, hi)
+        # the oracle starts from the SAME initial velocity: the slab's rows (its two ghost rows included) of u, v as the
+        # vortex kernel left them, collected on rank 0
+        s_lo, s_hi = r0, r0 + nrows_cpu + 2                                       # ghost-inclusive global rows of the slab
+        o_lo = jb if rank > 0 else 0                                               # rows this rank answers for
+        o_hi = je if rank < world - 1 else inp.ny
+        c_lo, c_hi = max(s_lo, o_lo), min(s_hi, o_hi)
+        ic_part = None
+        if c_hi > c_lo:
+            ic_part = {"rows": (c_lo, c_hi)}
+            for k in ("u", "v"):
+                f = s.get(k).reshape(-1, inp.nx)
+                ic_part[k] = f[c_lo - (jb - 1): c_hi - (jb - 1)].copy()
+                del f
+        if world > 1:
+            ic_all = [None] * world
+            dist.gather_object(ic_part, ic_all if rank == 0 else None, dst=0)
+        else:
+            ic_all = [ic_part]
+        parity_ic = None
+        if rank == 0:
+            parity_ic = {k: np.empty((s_hi - s_lo, inp.nx)) for k in ("u", "v")}
+            for part in ic_all:
+                if part:
+                    a_, b_ = part["rows"]
+                    for k in ("u", "v"):
+                        parity_ic[k][a_ - s_lo: b_ - s_lo] = part[k]
+        del ic_part, ic_all
+        a0, b0 = one_step()
+        warm_done = 1
+        mine = {}
+        rows = [j for j in range(max(lo, jb), min(hi, je))]
+        for k in ("u", "v", "p"):
+            f = s.get(k)
+            mine[k] = dict(zip(rows, row_digests(f, inp.nx, [j - (jb - 1) for j in rows]))) if rows else {}
+            del f
+        mine["counts"] = (a0.ad_iters, b0.ppe_sweeps)
+        if world > 1:
+            allm = [None] * world
+            dist.gather_object(mine, allm if rank == 0 else None, dst=0)
+        else:
+            allm = [mine]
+        if rank == 0:
+            parity_gpu = {k: {} for k in ("u", "v", "p")}
+            for m in allm:
+                for k in ("u", "v", "p"):
+                    parity_gpu[k].update(m[k])
+            parity_gpu["counts"] = [m["counts"] for m in allm]
+            parity_gpu["rows"] = (lo, hi, r0)
+
+    for _ in range(max(0, args.warmup - warm_done)):
         one_step()
     sampler = ClockSampler(dev)
     barrier()
@@ -377,7 +584,7 @@ def main():
     wall = time.perf_counter() - t0
     launches = s.launch_count - l0
     clocks = sampler.stop()
-    # device time of the step = CUDA-event stage timers (both stages run on the solver's stream back to back)
+    # device time of the stages = CUDA-event stage timers (the source-term / face kernels between the stages are not inside)
     dev_ms = float(np.mean(ad_ms) + np.mean(ppe_ms) + np.mean(cor_ms) + np.mean(ib_ms))
     if world > 1:
         t = torch.tensor([dev_ms, wall * 1e3 / args.steps], device="cuda")
@@ -388,27 +595,32 @@ def main():
     cells = ncx * ncy if not args.emulate_slab_of else ncx * (je - jb)
     value = cells / (wall_ms * 1e-3) / 1e6
 
-    # ---- roofline of the dominant kernel (k_ad_jacobi: 25 launches/step vs ~51 Poisson launches of 1/3 the bytes)
+    # ---- roofline of the dominant kernel BY TIME: the Poisson sweep (k_ppe + 1 launches of 25 B/cell per step against
+    # k_ad predictor launches of 49 B/cell).  achieved = algorithmic bytes / CUDA-event time per launch (events around
+    # the Poisson stage / around the predictor's sweep launches, ifx_step_stats).  Both fractions: against the copy
+    # bandwidth measured on this pool's B200s (MEASURED_PEAKS.json) and against north_star's nominal 8 TB/s.
     peak, peak_src = peaks()
     cells_local = ncx * (je - jb)
-    # CUDA events around the k_ad sweep launches alone (ifx_step_stats.ms_ad_sweeps; with bodies the per-iteration
-    # ghost-cell kernels, a few microseconds each, are inside)
     ad_launch_ms = float(np.mean(sweep_ms)) / k_ad if k_ad else None
     jac_bytes = 49.0 * cells_local               # read u,v,sx,sy + write u',v' (48 B/cell) + 1 B cell type
     ppe_launch_ms = float(np.mean(ppe_ms)) / (k_ppe + 1)
-    ppe_b_cell = 25 if full else 16              # full: read p, rhs, cell type; write p' — reference Laplace: read p, write p'
+    ppe_b_cell = 25 if full else 16              # full: read p, rhs, face mask; write p' — reference Laplace: read p, write p'
     ppe_bytes = float(ppe_b_cell) * cells_local
     ach_ad = jac_bytes / (ad_launch_ms * 1e-3) / 1e9 if ad_launch_ms else 0.0
     ach_ppe = ppe_bytes / (ppe_launch_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "k_sweep_v4<predictor Jacobi>", "achieved": ach_ad, "peak": peak, "unit": "GB/s",
-                "frac": ach_ad / peak, "traffic": measured_traffic("k_sweep_v4_ad", ncx, ncy) if world == 1 else None,
-                "peak_source": peak_src,
-                "algorithmic_bytes_per_cell": 49, "ms_per_launch": ad_launch_ms,
-                "poisson": {"kernel": "k_sweep_v4<poisson %s>" % ("general" if full else "laplace"), "achieved": ach_ppe,
-                            "traffic": measured_traffic("k_sweep_v4_ppe_general" if full else "k_sweep_v4_ppe_laplace", ncx, ncy)
-                            if world == 1 else None,
-                            "frac": ach_ppe / peak, "algorithmic_bytes_per_cell": ppe_b_cell, "ms_per_launch": ppe_launch_ms,
-                            "sweeps_per_s": 1e3 / ppe_launch_ms},
+    ppe_share = float(np.mean(ppe_ms)) / wall_ms
+    ad_share = float(np.mean(sweep_ms)) / wall_ms
+    roofline = {"bound": "hbm", "kernel": "k_sweep_v4<poisson %s>" % ("general" if full else "laplace"),
+                "achieved": ach_ppe, "peak": peak, "unit": "GB/s", "frac": ach_ppe / peak,
+                "frac_nominal_8tbs": ach_ppe / 8000.0,
+                "traffic": measured_traffic("k_sweep_v4_ppe_general" if full else "k_sweep_v4_ppe_laplace", ncx, ncy) if world == 1 else None,
+                "peak_source": peak_src, "algorithmic_bytes_per_cell": ppe_b_cell, "ms_per_launch": ppe_launch_ms,
+                "launches_per_step": k_ppe + 1, "share_of_step": ppe_share, "sweeps_per_s": 1e3 / ppe_launch_ms,
+                "predictor": {"kernel": "k_sweep_v4<predictor Jacobi>", "achieved": ach_ad, "frac": ach_ad / peak,
+                              "frac_nominal_8tbs": ach_ad / 8000.0,
+                              "traffic": measured_traffic("k_sweep_v4_ad", ncx, ncy) if world == 1 else None,
+                              "algorithmic_bytes_per_cell": 49, "ms_per_launch": ad_launch_ms, "launches_per_step": k_ad,
+                              "share_of_step": ad_share},
                 "projection_ms": float(np.mean(cor_ms)), "iblank_ghost_cells_ms": float(np.mean(ib_ms)),
                 "ghost_cells": int(s.lib.ifx_ghost_cell_count(s._h))}
 
@@ -491,19 +703,68 @@ def main():
                 dist.barrier()                     # nobody frees a segment a neighbour may still be storing into
             for h in sims:
                 h.close()
+        del host_in, host_out
 
     line = {"metric": METRIC, "value": value, "unit": METRIC, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": wall_ms, "device_ms_per_step": dev_ms, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
             "iters": {"ad": k_ad, "ppe_sweeps": k_ppe}, "roofline": roofline, "gpu_launches": launches,
             "clocks": clocks, "e2e": e2e}
-    if rank == 0 and not args.no_cpu_baseline:
-        cb = cpu_reference_arm(args, args.cpu_sample_rows, 1, 1)
-        line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    if slab_parity is not None or world > 1:
+        line["slab_parity"] = slab_parity["bit_exact"] if slab_parity else None
+        line["slab_parity_detail"] = slab_parity
     s.close()
+    if world > 1:
+        dist.barrier()
+
+    # ---- rank 0: the CPU arm (N = 1: timed as `cpu_baseline`; its first step doubles as the parity oracle; N > 1: the
+    # first step only) and the reference's own CUDA binary (N = 1)
     if rank == 0:
+        want_cb = world == 1 and not args.no_cpu_baseline
+        cb = None
+        if want_cb or parity_gpu is not None:
+            cb = cpu_reference_arm(args, args.cpu_sample_rows, 2 if want_cb else 0, 1, keep_first_step=parity_gpu is not None,
+                                   ic=parity_ic if parity_gpu is not None else None)
+        if want_cb:
+            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "sample_fraction")}
+        if parity_gpu is not None:
+            lo, hi, r0 = parity_gpu["rows"]
+            gnx, gny = cb["grid"]
+            bad, checked = {}, 0
+            for k in ("u", "v", "p"):
+                want = dict(zip(range(lo, hi), row_digests(cb["first_step"][k], gnx, [j - r0 for j in range(lo, hi)])))
+                bad[k] = sum(1 for j in range(lo, hi) if parity_gpu[k].get(j) != want[j])
+                checked += hi - lo
+            k_or = (args.ad_itermax, args.ppe_sweeps)
+            counts_ok = all(tuple(c) == k_or for c in parity_gpu["counts"])
+            line["parity_check"] = {
+                "bit_exact": all(v == 0 for v in bad.values()) and counts_ok,
+                "rows": hi - lo, "global_rows": [lo, hi], "cells": (hi - lo) * ncx, "fields": ["u", "v", "p"],
+                "mismatching_rows": bad, "iteration_counts_equal": counts_ok,
+                "what": f"first step of the timed workload (all {world} rank(s)) vs the CPU oracle run on cell rows {r0}..{r0 + cb['grid'][1] - 2}: "
+                        f"rows at least {PARITY_MARGIN} cells inside the oracle's slab (its artificial walls cannot reach them in "
+                        f"one step), every interior column, compared as per-row digests"}
+        if world == 1 and not args.no_ref_cuda and not args.emulate_slab_of:
+            rcu = ref_cuda_baseline(args)
+            if "unavailable" not in rcu and args.nx <= args.ny:
+                # the same work on our path: predictor only, no body, reference-compatible arithmetic (bit-identical results,
+                # tests/test_gpu_reference_parity.py)
+                inp_r = ifx.make_input(ncx, ncy, args.dt, args.Re, AD_itermax=args.ad_itermax, PPE_itermax=1)
+                with ifx.ImmerseFlow(inp_r, xf, yf, device=dev, compat=ifx.IFX_COMPAT_REFERENCE) as hr:
+                    hr.initializeData()
+                    hr.ADsolver()
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                    for _ in range(3):
+                        hr.ADsolver()
+                    torch.cuda.synchronize()
+                    tr = (time.perf_counter() - t0) / 3
+                rcu["ours_same_work"] = {"ms_per_step": tr * 1e3, "value": ncx * ncy / tr / 1e6, "unit": METRIC,
+                                         "what": "ifx_ad_solve in IFX_COMPAT_REFERENCE (predictor only, same bits)"}
+            line["ref_cuda_baseline"] = rcu
         print(json.dumps(line))
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

@@ -764,6 +764,7 @@ int ifx::run_ad_loop(ifx_solver* s, ifx_step_stats* st, bool full) {
   // step refreshes anyway, whereas the reference-compatible step reads that ring as the reference left it (App. A Q5).
   const bool lag = slabs && full;
   bool lag_first = true;
+  const int no_exchange = std::getenv("IFX_EXP_NO_RESIDUAL_EXCHANGE") ? 1 : 0;     // timing diagnostic only
   unsigned seq_before = s->seq[0];
   // ghost cells on slabs: sweep -> ghost-cell kernel (reads the neighbours' previous iterate) -> push kernel, which
   // re-delivers the boundary rows (now with their ghost cells) and only then publishes the sweep's sequence number
@@ -776,6 +777,7 @@ int ifx::run_ad_loop(ifx_solver* s, ifx_step_stats* st, bool full) {
     ja.uT = s->u[src ^ 1]; ja.vT = s->v[src ^ 1];
     ja.rc.eval_iter = m;
     ja.rc.lag = lag ? 1 : 0; ja.rc.lag_first = lag_first ? 1 : 0;
+    ja.rc.no_exchange = no_exchange;
     lag_first = false;
     const int fo[2] = {src ^ 1, 2 + (src ^ 1)};
     make_halo_ctx(s, 0, 2, fo, &ja.hx);
@@ -933,6 +935,7 @@ int ifx::run_ppe_loop(ifx_solver* s, ifx_step_stats* st, bool laplace_ref) {
     const int np = s->np;
     const bool lag = slabs && !sor;
     bool lag_first = true;
+    const int no_exchange = std::getenv("IFX_EXP_NO_RESIDUAL_EXCHANGE") ? 1 : 0;   // timing diagnostic only
     const int partner = (base + 1) % np;      // SOR: the other buffer of the pair
     auto set_sweep = [&](int m) {     // sweep m: iterate m-1 -> iterate m, evaluates residual(iterate m-1)
       const int src = sor ? base : (base + m - 1) % np;
@@ -941,6 +944,7 @@ int ifx::run_ppe_loop(ifx_solver* s, ifx_step_stats* st, bool laplace_ref) {
       pa.rc.eval_iter = m - 1;
       pa.rc.decide = decide;
       pa.rc.lag = lag ? 1 : 0; pa.rc.lag_first = lag_first ? 1 : 0;
+      pa.rc.no_exchange = no_exchange;
       lag_first = false;
       pa.sor_colour = 0;
       const int fo[1] = {4 + dst};

@@ -19,6 +19,7 @@ struct ReduceCfg {
   int lag;          // slabs: post this launch's partials, decide on the PREVIOUS launch's (no cross-GPU wait on the
                     // critical path); the loop's last launch is decided by a flush kernel (launch_lag_flush)
   int lag_first;    // lag: first launch of the loop or after a flush — nothing to decide yet
+  int no_exchange;  // diagnostic (IFX_EXP_NO_RESIDUAL_EXCHANGE): every rank decides on its own sum — timing only
   double tol;
   double band;      // relative half-width of the rounding band (times the abs-sum)
 };
@@ -88,16 +89,21 @@ static __device__ __noinline__ void slab_post_partial(const HaloCtx& hx, unsigne
     double* m = hx.mail[r] + ((size_t)slot * IFX_MAX_RANKS + me) * IFX_MAIL_VALS;
     m[0] = a; m[1] = b;
   }
+  // message passing: data, ONE system-scope fence, then the tags as relaxed stores (a release store per rank would
+  // pay the NVLink round trip eight times over, at the tail of every launch, with one thread of one CTA running)
   __threadfence_system();
-  for (int r = 0; r < hx.nranks; ++r) st_release_sys(hx.mail_seq[r] + slot * IFX_MAX_RANKS + me, tag);
+  for (int r = 0; r < hx.nranks; ++r) st_relaxed_sys(hx.mail_seq[r] + slot * IFX_MAX_RANKS + me, tag);
 }
 static __device__ __noinline__ void slab_collect_partials(const HaloCtx& hx, unsigned tag, double& a, double& b) {
   const unsigned slot = tag & (IFX_MAIL_SLOTS - 1);
   const unsigned me = (unsigned)hx.rank;
   double ga = 0.0, gb = 0.0;
-  for (int r = 0; r < hx.nranks; ++r) {
+  for (int r = 0; r < hx.nranks; ++r) {      // all tags (relaxed polls), ONE fence, then the data
     const unsigned* q = hx.mail_seq[me] + slot * IFX_MAX_RANKS + r;
-    while (ld_acquire_sys(q) != tag) { __nanosleep(64); }
+    while (ld_relaxed_sys(q) != tag) { __nanosleep(32); }
+  }
+  __threadfence_system();
+  for (int r = 0; r < hx.nranks; ++r) {
     const volatile double* m = hx.mail[me] + ((size_t)slot * IFX_MAX_RANKS + r) * IFX_MAIL_VALS;
     ga += m[0]; gb += m[1];
   }
@@ -166,7 +172,7 @@ __device__ __forceinline__ void block_reduce_and_decide(double r0, double r1, do
     ctl->ticket = 0;
     int eval_iter = rc.eval_iter;
     bool decide = true;
-    if (hx && hx->nranks > 1) {
+    if (hx && hx->nranks > 1 && !rc.no_exchange) {
       slab_post_partial(*hx, hx->mseq, a, b);
       if (rc.lag) {                        // the previous launch's sums (every rank posted them a sweep ago)
         eval_iter -= 1;

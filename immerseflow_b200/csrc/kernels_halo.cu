@@ -43,7 +43,7 @@ static __global__ void k_halo_wait(const unsigned* wait_lo, const unsigned* wait
 // has no successor, so this one-thread kernel collects its partials and decides.  Every rank runs it at the same
 // point of the same launch sequence and adds the same operands in the same order: same decision everywhere.
 static __global__ void k_lag_flush(LoopCtl* ctl, ReduceCfg rc, HaloCtx hx) {
-  if (threadIdx.x != 0 || ctl->done) return;
+  if (threadIdx.x != 0 || ctl->done || rc.no_exchange) return;
   double a = 0.0, b = 0.0;
   slab_collect_partials(hx, hx.mseq, a, b);
   decide_on_residual(ctl, rc, rc.eval_iter, a, b);

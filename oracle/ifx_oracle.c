@@ -21,6 +21,10 @@
 
 #define ID(i, j, nx) ((i) + (j) * (nx))
 
+/* bench.py sets the thread count explicitly: torchrun exports OMP_NUM_THREADS=1 to its workers */
+void orc_set_num_threads(int n) {
+  if (n > 0) omp_set_num_threads(n);
+}
 int orc_num_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

@@ -107,6 +107,7 @@ int orc_PPESolver_tol(int nx, int ny, const double* dx, const double* dy,
 int orc_write_results_to_file(const double* x, const double* y, const double* data,
                               int ni, int nj, const char* filename);
 
+void orc_set_num_threads(int n);    /* explicit OpenMP thread count (launchers may export OMP_NUM_THREADS=1) */
 int orc_num_threads(void);
 
 /* ================================================================================================

@@ -9,8 +9,10 @@ from conftest import ROOT
 
 
 def test_reference_arm_prints_the_contract_line():
+    # torchrun exports OMP_NUM_THREADS=1 to its workers: the CPU arm must use every host thread regardless
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--nx", "256", "--ny", "256",
-                        "--steps", "1", "--warmup", "1", "--cpu-sample-rows", "64"], capture_output=True, text=True, timeout=300)
+                        "--steps", "2", "--warmup", "1", "--cpu-sample-rows", "64"], capture_output=True, text=True, timeout=300,
+                       env=dict(os.environ, OMP_NUM_THREADS="1"))
     assert r.returncode == 0, r.stderr
     lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
     assert len(lines) == 1
@@ -20,7 +22,10 @@ def test_reference_arm_prints_the_contract_line():
         assert k in d, k
     assert d["impl"] == "reference" and d["metric"] == "Mcell-steps/s" and d["dtype"] == "f64" and d["vs_baseline"] is None
     assert d["value"] > 0 and d["higher_is_better"] is True
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] == d["value"]
+    assert d["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0)), "the CPU arm must not inherit OMP_NUM_THREADS=1"
+    assert d["steps"] == 2 and d["warmup"] == 1, "same steps / warm-up as asked for"
+    assert d["cpu_baseline"]["sample_fraction"] == 64 / 256
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and "model" not in d["config"]
 

@@ -2,7 +2,10 @@
 """Time the REFERENCE's own CUDA build (oracle/_ref/immerseFlow_ref: its unmodified translation units, file output
 stubbed) on one GPU — the "reference CUDA build on one B200" baseline of north_star.  Reported, not a target.
 
-Per-step time = (wall(tmax = a) - wall(tmax = b)) / (a - b): process start-up, allocation and grid I/O cancel.
+Per-step time = the spacing of the reference's own `iter = <AD_itermax> ...` lines (the last Jacobi iteration of every
+time step, ADSolver.cu:369), time-stamped as they arrive on a line-buffered pipe (`stdbuf -oL`): process start-up,
+allocation and grid I/O are outside.  (Differencing the wall time of two runs does not work: start-up takes 5-6 s at
+16384 x 16384 and varies by more than a step from run to run.)
 The reference runs only its predictor per time step (src/main.cu:93-96), with its own per-step cudaMalloc/cudaFree
 (ADSolver.cu:275-287) and a cudaDeviceSynchronize after every launch — all of that is part of what is timed.
 """
@@ -55,16 +58,28 @@ def write_grid(path, n_cells):
 
 
 def run(nx, ny, itmax, dt, Re, tmax, workdir):
+    """-> (wall seconds, number of `iter = ` lines, arrival times of the `iter = <itmax>` lines = end of every step)"""
     with open(os.path.join(workdir, "inputs", "inputs.txt"), "w") as f:
         f.write(INPUTS.format(nx=nx, ny=ny, itmax=itmax, tmax=tmax, dt=dt, Re=Re))
+    cmd = [REF]
+    if shutil.which("stdbuf"):
+        cmd = ["stdbuf", "-oL"] + cmd
     t0 = time.perf_counter()
-    r = subprocess.run([REF], cwd=os.path.join(workdir, "src"), env=dict(os.environ, IFX_REF_SAVE="none"),
-                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    p = subprocess.Popen(cmd, cwd=os.path.join(workdir, "src"), env=dict(os.environ, IFX_REF_SAVE="none"),
+                         stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, bufsize=1)
+    iters, ends = 0, []
+    last = f"iter = {itmax} "
+    for line in p.stdout:
+        if line.startswith("iter = "):
+            iters += 1
+            if line.startswith(last):
+                ends.append(time.perf_counter() - t0)
+    err = p.stderr.read()
+    rc = p.wait()
     t = time.perf_counter() - t0
-    if r.returncode != 0:
-        raise RuntimeError(r.stderr[-500:])
-    iters = r.stdout.count("iter = ")
-    return t, iters
+    if rc != 0:
+        raise RuntimeError(err[-500:])
+    return t, iters, ends
 
 
 def main():
@@ -74,7 +89,7 @@ def main():
     ap.add_argument("--ad-itermax", type=int, default=25)
     ap.add_argument("--dt", type=float, default=1e-3)
     ap.add_argument("--Re", type=float, default=150.0)
-    ap.add_argument("--steps-a", type=int, default=3)
+    ap.add_argument("--steps-a", type=int, default=4)
     ap.add_argument("--steps-b", type=int, default=1)
     a = ap.parse_args()
     if not os.path.exists(REF):
@@ -86,15 +101,16 @@ def main():
             os.makedirs(os.path.join(w, d))
         write_grid(os.path.join(w, "inputs", "xgrid.dat2"), a.nx)
         write_grid(os.path.join(w, "inputs", "ygrid.dat2"), a.ny)
-        tb, ib = run(a.nx, a.ny, a.ad_itermax, a.dt, a.Re, a.steps_b, w)
-        ta, ia = run(a.nx, a.ny, a.ad_itermax, a.dt, a.Re, a.steps_a, w)
-        per_step = (ta - tb) / (a.steps_a - a.steps_b)
-        k = (ia - ib) / (a.steps_a - a.steps_b)
+        ta, ia, ends = run(a.nx, a.ny, a.ad_itermax, a.dt, a.Re, a.steps_a, w)
+        if len(ends) < 2:
+            raise RuntimeError("the reference did not report the end of at least two steps (converged before AD_itermax?)")
+        per_step = (ends[-1] - ends[0]) / (len(ends) - 1)
+        k = ia / a.steps_a
         print(json.dumps({"impl": "reference CUDA build (unmodified TUs, nvcc -arch=sm_100, file output stubbed)",
                           "grid": [a.nx, a.ny], "predictor_iterations_per_step": k, "s_per_step": per_step,
                           "Mcell_steps_per_s": a.nx * a.ny / per_step / 1e6,
                           "note": "the reference's time step is the predictor only (src/main.cu:93-96)",
-                          "wall_s": {"steps_%d" % a.steps_a: ta, "steps_%d" % a.steps_b: tb}}))
+                          "step_end_times_s": ends, "wall_s": ta}))
     finally:
         shutil.rmtree(w, ignore_errors=True)
 
