@@ -46,6 +46,12 @@ def parse_args():
     ap.add_argument("--no-parity-check", action="store_true",
                     help="skip the bit-for-bit check of the timed workload's first step against the CPU oracle (rank 0) and, on "
                          "more than one GPU, of a slab run against a single-GPU run")
+    ap.add_argument("--ppe-pairs", type=int, default=0,
+                    help="1: two Jacobi sweeps per pass over memory in the Poisson solve (ifx_options.ppe_pairs; single GPU; measured "
+                         "bit-identical and NOT faster, profiles/r2_pair_kernel.md)")
+    ap.add_argument("--no-secondary", action="store_true",
+                    help="skip the short runs of BASELINE.json's other configurations (cavity 1024^2, cylinder 4096x2048, converged "
+                         "pressure solves) that the default single-GPU run appends under `configs`")
     ap.add_argument("--no-ref-cuda", action="store_true",
                     help="skip timing the reference's own CUDA build (oracle/_ref/immerseFlow_ref) on this GPU")
     ap.add_argument("--no-e2e", action="store_true")
@@ -359,6 +365,142 @@ def measured_traffic(kernel: str, nx: int, ny: int):
     return None
 
 
+def secondary_configs(ifx, torch, dev, args):
+    """BASELINE.json's other configurations on ONE GPU, each for a few steps (bounded: well under a minute in total), so that
+    the driver's record carries them too: configs[1] (lid-driven cavity, uniform 1024 x 1024 — L2-resident, launch-latency
+    bound), configs[2] (cylinder on the stretched 4096 x 2048 grid, checked against the CPU oracle in every cell), and steps
+    whose pressure solve actually CONVERGES (multigrid; point Jacobi never gets there) — to the reference's criterion with the
+    tolerance scaled per cell and capped at 0.5: its residual is an un-normalised sum and its loop starts from a residual of
+    1.0 (PPESolver.cu:170-172), so a tolerance of 1 or more means "no sweep"."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import make_case
+    out = []
+
+    def digits(f):
+        return np.array([float(f"{v:.7E}") for v in f])          # the grid files carry 7 significant digits
+
+    def run(name, what, ncx, ncy, xf, yf, dt, Re, *, bodies=None, vel=None, bc=None, ic="vortex", ppe_solver=1, ppe_itermax=50,
+            ppe_tol=0.0, ad_tol=None, steps=5, warmup=2, moving=0, lx=1.0, ly=1.0, extra=None):
+        inp = ifx.make_input(ncx, ncy, dt, Re, AD_itermax=args.ad_itermax, PPE_itermax=ppe_itermax, Lx=lx, Ly=ly)
+        rec = {"name": name, "what": what, "grid": [ncx, ncy], "ppe_solver": ppe_solver}
+        try:
+            with ifx.ImmerseFlow(inp, xf, yf, device=dev, compat=ifx.IFX_COMPAT_FULL, ppe_abs_residual=1, ppe_solver=ppe_solver,
+                                 ppe_tol=ppe_tol, ad_tol=ad_tol, bc=bc, sweeps_per_batch=ppe_itermax + 1) as h:
+                h.initializeData()
+                n = inp.nx * inp.ny
+                if ic == "zero":
+                    h.set("u", np.zeros(n)); h.set("v", np.zeros(n))
+                elif ic == "uniform":
+                    h.set("u", np.ones(n)); h.set("v", np.zeros(n))
+                stepno = 0
+
+                def one():
+                    nonlocal stepno
+                    if bodies is not None and (moving or stepno == 0):
+                        b, v_ = bodies(stepno) if callable(bodies) else (bodies, vel)
+                        h.set_bodies(b, v_)
+                    stepno += 1
+                    return h.step()
+                for _ in range(warmup):
+                    one()
+                torch.cuda.synchronize()
+                l0, t0 = h.launch_count, time.perf_counter()
+                sts = [one() for _ in range(steps)]
+                torch.cuda.synchronize()
+                t = (time.perf_counter() - t0) / steps
+                k_ppe = float(np.mean([q.ppe_sweeps for q in sts]))
+                rec.update({"ms_per_step": t * 1e3, "value": ncx * ncy / t / 1e6, "unit": METRIC, "steps": steps, "warmup": warmup,
+                            "gpu_launches_per_step": (h.launch_count - l0) / steps,
+                            "predictor_iterations": float(np.mean([q.ad_iters for q in sts])),
+                            "poisson_iterations": k_ppe, "poisson_residual": float(sts[-1].ppe_residual), "poisson_tolerance": ppe_tol,
+                            "poisson_converged": bool(ppe_tol > 0 and sts[-1].ppe_residual <= ppe_tol),
+                            "ms_poisson": float(np.mean([q.ms_ppe for q in sts])), "ms_predictor": float(np.mean([q.ms_ad for q in sts])),
+                            "ghost_cells": int(h.lib.ifx_ghost_cell_count(h._h))})
+                if ppe_solver == 1:
+                    rec["us_per_poisson_sweep"] = rec["ms_poisson"] * 1e3 / (k_ppe + 1)
+                    rec["us_per_predictor_sweep"] = float(np.mean([q.ms_ad_sweeps for q in sts])) * 1e3 / max(rec["predictor_iterations"], 1)
+                if extra:
+                    rec.update(extra)
+        except Exception as ex:       # noqa: BLE001 — a secondary line never takes the headline down
+            rec["error"] = f"{type(ex).__name__}: {ex}"[:300]
+        out.append(rec)
+        return rec
+
+    # ---- configs[1]: lid-driven cavity Re = 1000 (input-file Re = 2000: the predictor keeps the reference's factor 1/2)
+    n1 = 1024
+    xf1 = ifx.uniform_faces(n1, 1.0)
+    dt1 = 0.25 / n1
+    lid = dict(u_bc_w=0.0, u_bc_e=0.0, u_bc_s=0.0, u_bc_n=1.0)
+    l2 = {"l2": "8 fields x 8.4 MB = 67 MB: the working set is L2-resident (126 MB), the sweeps run from L2 and the step is "
+                "launch-latency bound — HBM roofline fractions do not apply to this configuration"}
+    run("cavity1024", "BASELINE configs[1]: lid-driven cavity Re=1000, uniform 1024x1024, no body; 25 predictor iterations + 50 Jacobi "
+        "Poisson sweeps per step (the bench step)", n1, n1, xf1, xf1, dt1, 2000.0, bc=lid, ic="zero", steps=20, warmup=3, extra=l2)
+    run("cavity1024_converged", "configs[1], pressure solved to a grid-scaled tolerance by multigrid (PPE_Solver 4, V(2,2) cycles)",
+        n1, n1, xf1, xf1, dt1, 2000.0, bc=lid, ic="zero", ppe_solver=4, ppe_tol=min(0.5, 1e-9 * n1 * n1 / dt1), ad_tol=min(0.5, 4e-10 * n1 * n1),
+        steps=10, warmup=3, extra=l2)
+
+    # ---- configs[2]: circular cylinder Re = 300 on the stretched 4096 x 2048 grid (tools/make_case.py)
+    try:
+        tmp = tempfile.mkdtemp(prefix="ifx_case_")
+        case = make_case.build("cylinder", tmp, 1.0, 2)
+        import shutil
+        shutil.rmtree(tmp, ignore_errors=True)
+        ncx, ncy = case["cells"]
+        xf2, yf2 = digits(case["xf"]), digits(case["yf"])
+        dt2, re2 = case["dt"], case["Re_file"]
+        cyl = [np.ascontiguousarray(m) for m, _ in case["bodies"]]
+        par = None
+        if not args.no_parity_check:
+            # every interior cell of u, v, p after two steps + the iteration counts + the ghost-cell maps, vs the CPU oracle
+            import _oracle as orc
+            orc.lib().orc_set_num_threads(host_threads())
+            inp = ifx.make_input(ncx, ncy, dt2, re2, AD_itermax=args.ad_itermax, PPE_itermax=args.ppe_sweeps, Lx=40.0, Ly=20.0)
+            o = orc.FullSolver(xf2, yf2, dt2, re2, args.ad_itermax, args.ppe_sweeps, ppe_abs=1)
+            nn = inp.nx * inp.ny
+            with ifx.ImmerseFlow(inp, xf2, yf2, device=dev, compat=ifx.IFX_COMPAT_FULL, ppe_abs_residual=1) as h:
+                h.initializeData()
+                u0, v0 = np.ones(nn), np.zeros(nn)
+                h.set("u", u0); h.set("v", v0); o.set("u", u0); o.set("v", v0)
+                h.set_bodies(cyl, [(0.0, 0.0)]); o.set_bodies(cyl, [(0.0, 0.0)]); o.update_ib()
+                inner = np.zeros((inp.ny, inp.nx), bool); inner[1:-1, 1:-1] = True
+                inner = inner.reshape(-1)
+                bad, counts_ok = 0, True
+                for _ in range(2):
+                    st = h.step(); so = o.step()
+                    counts_ok = counts_ok and (st.ad_iters, st.ppe_sweeps) == (int(so[0]), int(so[3]))
+                    for k in ("u", "v", "p"):
+                        bad += int(np.count_nonzero(h.get(k)[inner] != o.get(k)[inner]))
+                g1, go = h.ghost_cells(), o.ghost_cells()
+                maps_ok = all(np.array_equal(g1[k], go[k]) for k in g1)
+            o.close()
+            par = {"bit_exact": bad == 0 and counts_ok and maps_ok, "cells": int(ncx * ncy), "steps": 2, "mismatching_values": bad,
+                   "iteration_counts_equal": counts_ok, "ghost_cell_maps_equal": maps_ok,
+                   "what": "u, v, p in every interior cell after each of two steps, iteration counts, ghost-cell index maps and weights "
+                           "vs the CPU oracle"}
+        run("cylinder4096x2048", "BASELINE configs[2]: circular cylinder Re=300 (D/dx = 256), stretched 4096x2048 grid on 40x20, "
+            "sharp-interface body; 25 predictor iterations + 50 Jacobi Poisson sweeps per step", ncx, ncy, xf2, yf2, dt2, re2,
+            bodies=cyl, vel=[(0.0, 0.0)], ic="uniform", steps=10, warmup=3, lx=40.0, ly=20.0,
+            extra={"parity_check": par, "l2": "8 fields x 67 MB = 0.54 GB: streams from HBM"})
+        run("cylinder4096x2048_converged", "configs[2], pressure solved to a grid-scaled tolerance by line-smoothed multigrid "
+            "(PPE_Solver 5: the point smoother stalls on cell aspect ratios of 30)", ncx, ncy, xf2, yf2, dt2, re2, bodies=cyl,
+            vel=[(0.0, 0.0)], ic="uniform", ppe_solver=5, ppe_itermax=60, ppe_tol=min(0.5, 1e-9 * ncx * ncy / dt2), ad_tol=min(0.5, 4e-10 * ncx * ncy),
+            steps=2, warmup=1, lx=40.0, ly=20.0)
+    except Exception as ex:       # noqa: BLE001
+        out.append({"name": "cylinder4096x2048", "error": f"{type(ex).__name__}: {ex}"[:300]})
+
+    # ---- the headline workload with a CONVERGED pressure solve (multigrid, bodies re-classified every step)
+    nxm, nym = args.nx, args.ny
+    if args.mode == "full" and nxm * nym <= 16384 * 16384:
+        dtm = args.dt
+        xfm, yfm = ifx.uniform_faces(nxm, 1.0), ifx.uniform_faces(nym, 1.0)
+        run("workload_converged", f"the headline workload ({nxm}x{nym}, {args.bodies} moving bodies) with the pressure solved to a "
+            "grid-scaled tolerance by multigrid (PPE_Solver 4) instead of 50 Jacobi sweeps", nxm, nym, xfm, yfm, dtm, args.Re,
+            bodies=(lambda k: bodies_at(args.bodies, k, dtm)) if args.bodies else None, moving=1, ppe_solver=4, ppe_itermax=40,
+            ppe_tol=min(0.5, 1e-9 * nxm * nym / dtm), steps=2, warmup=1)
+    return out
+
+
 def slab_parity_check(ifx, slabs, dist, torch, rank, world, dev):
     """world > 1: a 2048 x 2048 full-mode run with moving bodies that straddle the slab boundaries, slab-decomposed
     over all ranks, against the same run on ONE GPU (rank 0): every owned row of u, v, p, bit for bit (row digests),
@@ -479,7 +621,8 @@ def main():
         """one simulation: handle, initial state, slab connections"""
         h = ifx.ImmerseFlow(inp, xf, yf, device=dev, sweeps_per_batch=args.ppe_sweeps + 1, rank=rank, nranks=world,
                             j_begin=jb, j_end=je, compat=ifx.IFX_COMPAT_FULL if full else ifx.IFX_COMPAT_REFERENCE,
-                            ppe_abs_residual=1 if full else 0, zero_copy_control=zero_copy_control)
+                            ppe_abs_residual=1 if full else 0, zero_copy_control=zero_copy_control,
+                            ppe_pairs=args.ppe_pairs if world == 1 else 0)
         h.initializeData()
         if not p0:                         # computed once, shared by the handles of the end-to-end pipeline
             p0.append(initial_pressure(inp.nx, inp.ny, jb - 1, h.field_size("p") // inp.nx))
@@ -762,6 +905,8 @@ def main():
                 rcu["ours_same_work"] = {"ms_per_step": tr * 1e3, "value": ncx * ncy / tr / 1e6, "unit": METRIC,
                                          "what": "ifx_ad_solve in IFX_COMPAT_REFERENCE (predictor only, same bits)"}
             line["ref_cuda_baseline"] = rcu
+        if world == 1 and not args.no_secondary and not args.emulate_slab_of and full:
+            line["configs"] = secondary_configs(ifx, torch, dev, args)
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

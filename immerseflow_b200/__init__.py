@@ -66,7 +66,7 @@ class IfxOptions(C.Structure):
                 ("bc", IfxBC), ("ad_tol", C.c_double), ("ppe_tol", C.c_double), ("ppe_abs_residual", C.c_int),
                 ("rank", C.c_int), ("nranks", C.c_int), ("j_begin", C.c_int), ("j_end", C.c_int),
                 ("sweeps_per_batch", C.c_int), ("use_graphs", C.c_int), ("ppe_solver", C.c_int), ("ppe_omega", C.c_double),
-                ("zero_copy_control", C.c_int), ("reserved", C.c_int * 4)]
+                ("zero_copy_control", C.c_int), ("ppe_pairs", C.c_int), ("reserved", C.c_int * 3)]
 
 
 class IfxStepStats(C.Structure):
@@ -226,7 +226,8 @@ class ImmerseFlow:
                  rank: int = 0, nranks: int = 1, j_begin: int = 0, j_end: int = 0,
                  sweeps_per_batch: int = 64, ppe_abs_residual: int = 0,
                  ad_tol: Optional[float] = None, ppe_tol: Optional[float] = None,
-                 ppe_solver: int = 0, ppe_omega: float = 0.0, zero_copy_control: int = 0, use_graphs: int = 0):
+                 ppe_solver: int = 0, ppe_omega: float = 0.0, zero_copy_control: int = 0, use_graphs: int = 0,
+                 ppe_pairs: int = 0):
         self.lib = load_library()
         self.Input = inp
         xf = np.ascontiguousarray(xf, dtype=np.float64)
@@ -241,6 +242,7 @@ class ImmerseFlow:
         opt.ppe_abs_residual = ppe_abs_residual
         opt.ppe_solver, opt.ppe_omega = ppe_solver, ppe_omega      # 2 line SOR, 3 red-black SOR, 4 / 5 multigrid (full mode)
         opt.zero_copy_control = zero_copy_control
+        opt.ppe_pairs = ppe_pairs                                  # two Jacobi sweeps per pass (opt-in, see immerseflow_c.h)
         opt.use_graphs = use_graphs
         if ad_tol is not None:
             opt.ad_tol = ad_tol

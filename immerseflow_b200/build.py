@@ -31,6 +31,7 @@ SOURCES = [
     ("kernels_ad.cu", True),
     ("kernels_ppe.cu", True),
     ("kernels_v4.cu", True),
+    ("kernels_pair.cu", True),
     ("kernels_reduce.cu", True),
     ("kernels_misc.cu", True),
     ("kernels_halo.cu", True),

@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <vector>
 
 using namespace ifx;
 
@@ -700,7 +701,8 @@ int ifx::exact_decide(ifx_solver* s, const ReduceCfg& rc, bool two_arrays) {
 int ifx::run_ad_loop(ifx_solver* s, ifx_step_stats* st, bool full) {
   const Layout& L = s->L;
   const bool exact = s->opt.reduce_mode == IFX_REDUCE_REFERENCE;
-  const int itermax = s->in.AD_itermax;
+  // the reference's loop starts from uRes = vRes = 1.0 (ADSolver.cu:313-315): a tolerance of 2 or more means no iteration
+  const int itermax = (1.0 + 1.0 > s->opt.ad_tol) ? s->in.AD_itermax : 0;
   const int ry = rows_per_cta_for(s, 2);
   const dim3 grid = tile_grid(s, ry, 2);
   const size_t nblocks = (size_t)grid.x * grid.y;
@@ -881,7 +883,8 @@ int ifx::enqueue_ppe_sweep(ifx_solver* s, PpeSweepArgs& a, dim3 grid, bool lapla
 int ifx::run_ppe_loop(ifx_solver* s, ifx_step_stats* st, bool laplace_ref) {
   const Layout& L = s->L;
   const bool exact = s->opt.reduce_mode == IFX_REDUCE_REFERENCE;
-  const int itermax = s->in.PPE_itermax;
+  // the reference's loop starts from res = 1.0 (PPESolver.cu:170-172): a tolerance of 1 or more means no sweep at all
+  const int itermax = (1.0 > s->opt.ppe_tol) ? s->in.PPE_itermax : 0;
   const int pmode = laplace_ref ? 0 : 1;
   const int ry = rows_per_cta_for(s, pmode);
   const dim3 grid = tile_grid(s, ry, pmode);
@@ -957,48 +960,140 @@ int ifx::run_ppe_loop(ifx_solver* s, ifx_step_stats* st, bool laplace_ref) {
       const int fo[1] = {4 + base};
       make_halo_ctx(s, 1, 1, fo, &pa.hx);
     };
-    int m = 0;
-    for (;;) {
-      const int todo = std::min(s->opt.sweeps_per_batch, itermax + 1 - m);
-      for (int b = 0; b < todo; b++) {
-        set_sweep(++m);
-        pa.force = 0;
-        if ((rc = enqueue_ppe_sweep(s, pa, grid, laplace_ref, exact)) != IFX_OK) return rc;
-        if (exact && m > 1 && (rc = exact_decide(s, pa.rc, false)) != IFX_OK) return rc;
-        if (sor) {
-          set_black();
-          if ((rc = enqueue_ppe_sweep(s, pa, grid, laplace_ref, false)) != IFX_OK) return rc;
-        }
-      }
-      if (lag) {
-        s->launches++;
-        IFX_CUDA(s, launch_lag_flush(s->ctl, pa.rc, pa.hx, s->stream));
-        lag_first = true;
-      }
-      if ((rc = fetch_ctl(s)) != IFX_OK) return rc;
-      if (s->h_ctl->done && s->h_ctl->ambiguous && !slabs) {
-        fallbacks++;
-        if ((rc = ensure_exact_buffers(s)) != IFX_OK) return rc;
-        pa.res = s->res_a;
-        m = s->h_ctl->iter + 1;          // the sweep that evaluated the ambiguous residual
-        set_sweep(m);
-        pa.force = 1; pa.rc.decide = 0;
-        if ((rc = enqueue_ppe_sweep(s, pa, grid, laplace_ref, true)) != IFX_OK) return rc;
-        if ((rc = exact_decide(s, pa.rc, false)) != IFX_OK) return rc;
-        pa.rc.decide = 1;
-        if ((rc = fetch_ctl(s)) != IFX_OK) return rc;
-        if (sor && !s->h_ctl->done) {    // not converged after all: the iteration's second half was skipped, run it
-          set_black();
+    if (sor) {
+      int m = 0;
+      for (;;) {
+        const int todo = std::min(s->opt.sweeps_per_batch, itermax + 1 - m);
+        for (int b = 0; b < todo; b++) {
+          set_sweep(++m);
           pa.force = 0;
+          if ((rc = enqueue_ppe_sweep(s, pa, grid, laplace_ref, exact)) != IFX_OK) return rc;
+          if (exact && m > 1 && (rc = exact_decide(s, pa.rc, false)) != IFX_OK) return rc;
+          set_black();
           if ((rc = enqueue_ppe_sweep(s, pa, grid, laplace_ref, false)) != IFX_OK) return rc;
         }
+        if ((rc = fetch_ctl(s)) != IFX_OK) return rc;
+        if (s->h_ctl->done && s->h_ctl->ambiguous && !slabs) {
+          fallbacks++;
+          if ((rc = ensure_exact_buffers(s)) != IFX_OK) return rc;
+          pa.res = s->res_a;
+          m = s->h_ctl->iter + 1;          // the sweep that evaluated the ambiguous residual
+          set_sweep(m);
+          pa.force = 1; pa.rc.decide = 0;
+          if ((rc = enqueue_ppe_sweep(s, pa, grid, laplace_ref, true)) != IFX_OK) return rc;
+          if ((rc = exact_decide(s, pa.rc, false)) != IFX_OK) return rc;
+          pa.rc.decide = 1;
+          if ((rc = fetch_ctl(s)) != IFX_OK) return rc;
+          if (!s->h_ctl->done) {           // not converged after all: the iteration's second half was skipped, run it
+            set_black();
+            pa.force = 0;
+            if ((rc = enqueue_ppe_sweep(s, pa, grid, laplace_ref, false)) != IFX_OK) return rc;
+          }
+        }
+        if (s->h_ctl->done) break;
+        if (m >= itermax + 1) return fail(s, IFX_ERR_STATE, "Poisson loop ran past PPE_itermax without a decision");
       }
-      if (s->h_ctl->done) break;
-      if (m >= itermax + 1) return fail(s, IFX_ERR_STATE, "Poisson loop ran past PPE_itermax without a decision");
+      K = s->h_ctl->iter;
+      s->cur_p = base;
+      if (slabs && (rc = halo_wait(s, 1, seq_before + (unsigned)(2 * K), tw_ppe)) != IFX_OK) return rc;
+    } else {
+      // ---- point Jacobi.  A launch starts from the newest stored iterate `it` (buffer `cur`) and is either a single
+      // sweep (it -> it+1, evaluates r(p_it)) or a PAIR (kernels_pair.cu: it -> it+2 in one pass over memory, evaluates
+      // r(p_it) and r(p_it+1); iterate it+1 exists in shared memory only).  where[k] = buffer holding iterate k, or -1.
+      std::vector<int> where((size_t)itermax + 4, -1);
+      std::vector<unsigned> seq_at((size_t)itermax + 4, seq_before);
+      where[0] = base;
+      int it = 0, cur = base;
+      const int nyi = L.je - L.jb;
+      const bool pairs = s->opt.ppe_pairs && !laplace_ref && !exact && !slabs && nyi >= 4;
+      PpeSweepArgs pp = pa;                            // pair launches: own tile geometry, 4 partial sums per CTA
+      dim3 grid2(1, 1, 1);
+      if (pairs) {
+        const int tw2 = pair_tile_cols();
+        const int ry2 = std::max(2, std::min(ry, 255));
+        int ty2 = (nyi + ry2 - 1) / ry2;
+        if (ty2 > 1 && nyi - (ty2 - 1) * ry2 == 1) ty2 -= 1;      // the last tile takes the odd row: never a 1-row tile
+        grid2 = dim3((L.nx - 2 + tw2 - 1) / tw2, ty2, 1);
+        if ((rc = ensure_partials(s, 2 * (size_t)grid2.x * grid2.y)) != IFX_OK) return rc;
+        pa.partials = s->partials;
+        pp = pa;
+        pp.rows_per_cta = ry2;
+        pp.rc.band = rounding_band(s, (size_t)grid2.x * grid2.y, 2 * (ry2 + 1));
+      }
+      // one launch; eval = index of the iterate whose residual it evaluates (single) / of the first of the two (pair)
+      auto launch = [&](bool pair, int src, int dst, int eval, int force, int decide_now, bool wres, bool exchange) -> int {
+        PpeSweepArgs& q = pair ? pp : pa;
+        q.pC = s->p[src]; q.pT = s->p[dst];
+        q.rc.eval_iter = eval;
+        q.rc.decide = decide_now;
+        q.rc.lag = (lag && exchange) ? 1 : 0; q.rc.lag_first = lag_first ? 1 : 0;
+        q.rc.no_exchange = exchange ? no_exchange : 1;
+        if (exchange) lag_first = false;
+        q.force = force;
+        q.sor_colour = 0;
+        const int fo[1] = {4 + dst};
+        make_halo_ctx(s, 1, 1, fo, &q.hx);
+        if (pair) {
+          s->launches++;
+          IFX_CUDA(s, launch_ppe_pair(q, grid2, s->stream));
+          return IFX_OK;
+        }
+        return enqueue_ppe_sweep(s, q, grid, laplace_ref, wres);
+      };
+      // re-create iterate k, which a pair only held in shared memory, from iterate k-1 (one forced single sweep)
+      auto recreate = [&](int k) -> int {
+        const int src = where[k - 1], dst = (src + 1) % np;
+        if (src < 0) return fail(s, IFX_ERR_STATE, "Poisson loop: the predecessor of an unstored iterate is gone");
+        int r2 = launch(false, src, dst, 0, 1, 0, false, false);
+        if (r2 != IFX_OK) return r2;
+        where[k] = dst; seq_at[k] = pa.hx.seq;
+        for (size_t z = (size_t)k + 1; z < where.size(); z++) where[z] = -1;
+        return IFX_OK;
+      };
+      const PpeSweepArgs* last = &pa;
+      for (;;) {
+        int launched = 0;
+        while (launched < s->opt.sweeps_per_batch && it <= itermax) {
+          const int dst = (cur + 1) % np;
+          const bool pair = pairs && it + 1 <= itermax;
+          if ((rc = launch(pair, cur, dst, it, 0, decide, exact, true)) != IFX_OK) return rc;
+          last = pair ? &pp : &pa;
+          if (exact && it >= 1 && (rc = exact_decide(s, pa.rc, false)) != IFX_OK) return rc;
+          it += pair ? 2 : 1;
+          where[it] = dst; seq_at[it] = last->hx.seq;
+          cur = dst;
+          launched++;
+        }
+        if (lag && launched > 0) {
+          s->launches++;
+          IFX_CUDA(s, launch_lag_flush(s->ctl, last->rc, last->hx, s->stream));
+          lag_first = true;
+        }
+        if ((rc = fetch_ctl(s)) != IFX_OK) return rc;
+        if (s->h_ctl->done && s->h_ctl->ambiguous && !slabs) {
+          // the fused sum of iterate q is within rounding of the tolerance: evaluate it in the reference's summation
+          // order — a forced single sweep from iterate q that writes the residual array (and iterate q+1)
+          fallbacks++;
+          if ((rc = ensure_exact_buffers(s)) != IFX_OK) return rc;
+          pa.res = s->res_a;
+          const int q = s->h_ctl->iter;
+          if (where[q] < 0 && (rc = recreate(q)) != IFX_OK) return rc;
+          const int src = where[q], dst = (src + 1) % np;
+          if ((rc = launch(false, src, dst, q, 1, 0, true, false)) != IFX_OK) return rc;
+          if ((rc = exact_decide(s, pa.rc, false)) != IFX_OK) return rc;
+          if ((rc = fetch_ctl(s)) != IFX_OK) return rc;
+          for (size_t z = (size_t)q + 1; z < where.size(); z++) where[z] = -1;
+          where[q + 1] = dst; seq_at[q + 1] = pa.hx.seq;
+          it = q + 1; cur = dst;
+        }
+        if (s->h_ctl->done) break;
+        if (it > itermax) return fail(s, IFX_ERR_STATE, "Poisson loop ran past PPE_itermax without a decision");
+      }
+      K = s->h_ctl->iter;
+      if (where[K] < 0 && (rc = recreate(K)) != IFX_OK) return rc;      // the rule fired on a pair's intermediate iterate
+      s->cur_p = where[K];
+      if (slabs && (rc = halo_wait(s, 1, seq_at[K], tw_ppe)) != IFX_OK) return rc;
     }
-    K = s->h_ctl->iter;
-    s->cur_p = sor ? base : (base + K) % np;
-    if (slabs && (rc = halo_wait(s, 1, seq_before + (unsigned)(sor ? 2 * K : K), tw_ppe)) != IFX_OK) return rc;
   }
   if (laplace_ref) {   // PPESolver.cu:195
     s->launches++;

@@ -128,7 +128,7 @@ int ifx::run_ppe_multigrid(ifx_solver* s, ifx_step_stats* st) {
   const Layout& L = s->L;
   if (s->opt.nranks != 1) return fail(s, IFX_ERR_INVALID, "multigrid is single-GPU for now");
   const bool exact = s->opt.reduce_mode == IFX_REDUCE_REFERENCE;
-  const int itermax = s->in.PPE_itermax;
+  const int itermax = (1.0 > s->opt.ppe_tol) ? s->in.PPE_itermax : 0;      // the loop starts from res = 1.0 (PPESolver.cu:170-172)
   const int ry = rows_per_cta_for(s, 1);
   const dim3 grid = tile_grid(s, ry, 1);
   const size_t nblocks = (size_t)grid.x * grid.y;
@@ -228,7 +228,7 @@ int ifx::run_ppe_lines(ifx_solver* s, ifx_step_stats* st) {
   const bool mg = s->opt.ppe_solver == 5;
   if (s->opt.nranks != 1) return fail(s, IFX_ERR_INVALID, "line relaxation is single-GPU for now");
   const bool exact = s->opt.reduce_mode == IFX_REDUCE_REFERENCE;
-  const int itermax = s->in.PPE_itermax;
+  const int itermax = (1.0 > s->opt.ppe_tol) ? s->in.PPE_itermax : 0;      // the loop starts from res = 1.0 (PPESolver.cu:170-172)
   const int ry = rows_per_cta_for(s, 1);
   const dim3 grid = tile_grid(s, ry, 1);
   const size_t nblocks = (size_t)grid.x * grid.y;

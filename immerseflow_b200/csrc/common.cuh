@@ -97,7 +97,7 @@ struct LoopCtl {
 #define IFX_MAX_TILES 1024
 #define IFX_SYNC_GROUPS 3          // 0: predictor sweeps (u, v), 1: Poisson sweeps (p), 2: everything else
 #define IFX_MAIL_SLOTS 8
-#define IFX_MAIL_VALS 4            // doubles per mailbox entry (two residual pairs: a launch may carry two sweeps)
+#define IFX_MAIL_VALS 6            // doubles per mailbox entry: two residual pairs, their count, the first iterate index
 #define IFX_SEG_FIELDS_MAX 8       // fields an exchange segment may hold: u[2], v[2], p[3] (+1 spare)
 #define IFX_GC_REACH 4             // rows beyond its slab a ghost-cell stencil may read from the neighbour's memory
 

@@ -82,32 +82,37 @@ struct PpeSweepArgs {
 // `tag`, waiting for stragglers).  A lock-step launch does both for its own tag; a LAGGED launch posts its own and
 // collects the previous launch's, which arrived a whole sweep ago — the ranks then drift by up to one launch instead
 // of meeting 76 times per step (profiles/r1_scaling.md).
-static __device__ __noinline__ void slab_post_partial(const HaloCtx& hx, unsigned tag, double a, double b) {
+// A mailbox entry carries up to two residual pairs (a launch of the pair kernel, kernels_pair.cu, evaluates two
+// iterates) and says so itself: {a0, b0, a1, b1, number of pairs, iterate index of the first pair}.
+static __device__ __noinline__ void slab_post_partial(const HaloCtx& hx, unsigned tag, const double* v, int npairs,
+                                                      int eval_first) {
   const unsigned slot = tag & (IFX_MAIL_SLOTS - 1);
   const unsigned me = (unsigned)hx.rank;
   for (int r = 0; r < hx.nranks; ++r) {
     double* m = hx.mail[r] + ((size_t)slot * IFX_MAX_RANKS + me) * IFX_MAIL_VALS;
-    m[0] = a; m[1] = b;
+    m[0] = v[0]; m[1] = v[1]; m[2] = v[2]; m[3] = v[3]; m[4] = (double)npairs; m[5] = (double)eval_first;
   }
   // message passing: data, ONE system-scope fence, then the tags as relaxed stores (a release store per rank would
   // pay the NVLink round trip eight times over, at the tail of every launch, with one thread of one CTA running)
   __threadfence_system();
   for (int r = 0; r < hx.nranks; ++r) st_relaxed_sys(hx.mail_seq[r] + slot * IFX_MAX_RANKS + me, tag);
 }
-static __device__ __noinline__ void slab_collect_partials(const HaloCtx& hx, unsigned tag, double& a, double& b) {
+static __device__ __noinline__ void slab_collect_partials(const HaloCtx& hx, unsigned tag, double* v, int& npairs,
+                                                          int& eval_first) {
   const unsigned slot = tag & (IFX_MAIL_SLOTS - 1);
   const unsigned me = (unsigned)hx.rank;
-  double ga = 0.0, gb = 0.0;
   for (int r = 0; r < hx.nranks; ++r) {      // all tags (relaxed polls), ONE fence, then the data
     const unsigned* q = hx.mail_seq[me] + slot * IFX_MAX_RANKS + r;
     while (ld_relaxed_sys(q) != tag) { __nanosleep(32); }
   }
   __threadfence_system();
-  for (int r = 0; r < hx.nranks; ++r) {
+  double g[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int r = 0; r < hx.nranks; ++r) {      // rank order: same operands, same order, same sums on every rank
     const volatile double* m = hx.mail[me] + ((size_t)slot * IFX_MAX_RANKS + r) * IFX_MAIL_VALS;
-    ga += m[0]; gb += m[1];
+    g[0] += m[0]; g[1] += m[1]; g[2] += m[2]; g[3] += m[3];
+    if (r == 0) { npairs = (int)m[4]; eval_first = (int)m[5]; }
   }
-  a = ga; b = gb;
+  v[0] = g[0]; v[1] = g[1]; v[2] = g[2]; v[3] = g[3];
 }
 
 // the stop decision on a pair of global residual sums (one thread)
@@ -129,25 +134,54 @@ __device__ __forceinline__ void decide_on_residual(LoopCtl* ctl, const ReduceCfg
     ctl->done = 1;
   }
 }
+// ... on the one or two iterates a launch evaluated, in order; the second only if the first did not end the loop
+__device__ __forceinline__ void decide_on_residuals(LoopCtl* ctl, const ReduceCfg& rc, int eval_first, int npairs, const double* v) {
+  decide_on_residual(ctl, rc, eval_first, v[0], v[1]);
+  if (npairs > 1 && !ctl->done) decide_on_residual(ctl, rc, eval_first + 1, v[2], v[3]);
+}
 
-template <int THREADS>
-__device__ __forceinline__ void block_reduce_and_decide(double r0, double r1, double* partials,
-                                                        LoopCtl* ctl, const ReduceCfg& rc,
-                                                        unsigned bid, unsigned nblocks, const HaloCtx* hx = nullptr) {
+// what the one thread that holds a launch's global-memory sums does with them: single GPU -> decide; slabs -> post
+// them, then decide on this launch's sums (lock step: wait for every rank) or on the PREVIOUS launch's (lagged)
+__device__ __forceinline__ void finish_residuals(LoopCtl* ctl, const ReduceCfg& rc, const HaloCtx* hx, double* v, int npairs) {
+  int eval_first = rc.eval_iter;
+  bool decide = true;
+  if (hx && hx->nranks > 1 && !rc.no_exchange) {
+    slab_post_partial(*hx, hx->mseq, v, npairs, eval_first);
+    if (rc.lag) {                        // the previous launch's sums (every rank posted them a sweep ago)
+      decide = !rc.lag_first;
+      if (decide) slab_collect_partials(*hx, hx->mseq - 1, v, npairs, eval_first);
+    } else {
+      slab_collect_partials(*hx, hx->mseq, v, npairs, eval_first);
+    }
+  }
+  if (decide) decide_on_residuals(ctl, rc, eval_first, npairs, v);
+}
+
+// NP = 1: (r[0], r[1]) is the residual pair of rc.eval_iter; NP = 2: (r[2], r[3]) in addition, of rc.eval_iter + 1
+template <int THREADS, int NP>
+__device__ __forceinline__ void block_reduce_and_decide_n(double (&r)[2 * NP], double* partials, LoopCtl* ctl,
+                                                          const ReduceCfg& rc, unsigned bid, unsigned nblocks,
+                                                          const HaloCtx* hx) {
   constexpr int NW = THREADS / 32;
-  __shared__ double sh[2][NW];
+  constexpr int NV = 2 * NP;
+  __shared__ double sh[NV][NW];
   __shared__ int s_last;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  r0 = warp_sum(r0);
-  r1 = warp_sum(r1);
-  if (lane == 0) { sh[0][warp] = r0; sh[1][warp] = r1; }
+#pragma unroll
+  for (int q = 0; q < NV; ++q) r[q] = warp_sum(r[q]);
+  if (lane == 0) {
+#pragma unroll
+    for (int q = 0; q < NV; ++q) sh[q][warp] = r[q];
+  }
   __syncthreads();
   if (threadIdx.x == 0) {
-    double a = sh[0][0], b = sh[1][0];
 #pragma unroll
-    for (int w = 1; w < NW; ++w) { a += sh[0][w]; b += sh[1][w]; }
-    partials[2 * bid] = a;
-    partials[2 * bid + 1] = b;
+    for (int q = 0; q < NV; ++q) {
+      double a = sh[q][0];
+#pragma unroll
+      for (int w = 1; w < NW; ++w) a += sh[q][w];
+      partials[NV * bid + q] = a;
+    }
     __threadfence();
     const unsigned t = atomicAdd(&ctl->ticket, 1u);
     s_last = (t == nblocks - 1);
@@ -155,36 +189,49 @@ __device__ __forceinline__ void block_reduce_and_decide(double r0, double r1, do
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  double a = 0.0, b = 0.0;
+  double acc[NV];
+#pragma unroll
+  for (int q = 0; q < NV; ++q) acc[q] = 0.0;
   for (unsigned k = threadIdx.x; k < nblocks; k += THREADS) {
-    a += __ldcg(partials + 2 * k);
-    b += __ldcg(partials + 2 * k + 1);
+#pragma unroll
+    for (int q = 0; q < NV; ++q) acc[q] += __ldcg(partials + NV * k + q);
   }
-  a = warp_sum(a);
-  b = warp_sum(b);
+#pragma unroll
+  for (int q = 0; q < NV; ++q) acc[q] = warp_sum(acc[q]);
   __syncthreads();
-  if (lane == 0) { sh[0][warp] = a; sh[1][warp] = b; }
+  if (lane == 0) {
+#pragma unroll
+    for (int q = 0; q < NV; ++q) sh[q][warp] = acc[q];
+  }
   __syncthreads();
   if (threadIdx.x == 0) {
-    a = sh[0][0]; b = sh[1][0];
+    double v[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-    for (int w = 1; w < NW; ++w) { a += sh[0][w]; b += sh[1][w]; }
-    ctl->ticket = 0;
-    int eval_iter = rc.eval_iter;
-    bool decide = true;
-    if (hx && hx->nranks > 1 && !rc.no_exchange) {
-      slab_post_partial(*hx, hx->mseq, a, b);
-      if (rc.lag) {                        // the previous launch's sums (every rank posted them a sweep ago)
-        eval_iter -= 1;
-        decide = !rc.lag_first;
-        if (decide) slab_collect_partials(*hx, hx->mseq - 1, a, b);
-      } else {
-        slab_collect_partials(*hx, hx->mseq, a, b);
-      }
+    for (int q = 0; q < NV; ++q) {
+      double a = sh[q][0];
+#pragma unroll
+      for (int w = 1; w < NW; ++w) a += sh[q][w];
+      v[q] = a;
     }
-    if (decide) decide_on_residual(ctl, rc, eval_iter, a, b);
+    ctl->ticket = 0;
+    finish_residuals(ctl, rc, hx, v, NP);
     __threadfence();
   }
+}
+
+template <int THREADS>
+__device__ __forceinline__ void block_reduce_and_decide(double r0, double r1, double* partials,
+                                                        LoopCtl* ctl, const ReduceCfg& rc,
+                                                        unsigned bid, unsigned nblocks, const HaloCtx* hx = nullptr) {
+  double r[2] = {r0, r1};
+  block_reduce_and_decide_n<THREADS, 1>(r, partials, ctl, rc, bid, nblocks, hx);
+}
+template <int THREADS>
+__device__ __forceinline__ void block_reduce_and_decide_pair(double a0, double a1, double b0, double b1, double* partials,
+                                                             LoopCtl* ctl, const ReduceCfg& rc, unsigned bid,
+                                                             unsigned nblocks, const HaloCtx* hx = nullptr) {
+  double r[4] = {a0, a1, b0, b1};
+  block_reduce_and_decide_n<THREADS, 2>(r, partials, ctl, rc, bid, nblocks, hx);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -200,6 +247,11 @@ cudaError_t launch_set_pressure_bc_ref(const Layout& L, double* p0, double* p1, 
 // kernels_v4.cu — the sweep kernels: bulk-copy row pipeline, lean interior path, in-line shared-reciprocal division
 cudaError_t launch_ad_jacobi_v4(const AdJacobiArgs& a, dim3 grid, cudaStream_t st, bool write_res);
 cudaError_t launch_ppe_sweep_v4(const PpeSweepArgs& a, dim3 grid, cudaStream_t st, bool laplace_ref, bool write_res);
+// kernels_pair.cu — two Jacobi sweeps of the general Poisson operator per pass over memory (opt-in, single GPU: measured
+// bit-identical but not faster, see the file's header); a.rc.eval_iter = index of the INPUT iterate; a.partials holds
+// 4 doubles per CTA
+cudaError_t launch_ppe_pair(const PpeSweepArgs& a, dim3 grid, cudaStream_t st);
+int pair_tile_cols();
 int v4_tile_cols(int mode /*0: Laplace, 1: general Poisson, 2: predictor*/);
 // kernels_full.cu — PPE source term, projection, BC refresh (IFX_COMPAT_FULL)
 cudaError_t launch_apply_ring(const Layout& L, double* q, const double* two_bc, int neumann, cudaStream_t st);

@@ -44,9 +44,10 @@ static __global__ void k_halo_wait(const unsigned* wait_lo, const unsigned* wait
 // point of the same launch sequence and adds the same operands in the same order: same decision everywhere.
 static __global__ void k_lag_flush(LoopCtl* ctl, ReduceCfg rc, HaloCtx hx) {
   if (threadIdx.x != 0 || ctl->done || rc.no_exchange) return;
-  double a = 0.0, b = 0.0;
-  slab_collect_partials(hx, hx.mseq, a, b);
-  decide_on_residual(ctl, rc, rc.eval_iter, a, b);
+  double v[4];
+  int npairs = 1, eval_first = rc.eval_iter;
+  slab_collect_partials(hx, hx.mseq, v, npairs, eval_first);
+  decide_on_residuals(ctl, rc, eval_first, npairs, v);
   __threadfence();
 }
 cudaError_t launch_lag_flush(LoopCtl* ctl, const ReduceCfg& rc, const HaloCtx& hx, cudaStream_t st) {

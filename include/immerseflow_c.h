@@ -112,7 +112,12 @@ typedef struct {
    * engine serves whole-field transfers ahead of a step's control copies and stalls it (measured on B200: a
    * concurrent download delays a 31 ms step by 16 ms; bench.py's end-to-end pipeline sets this). */
   int zero_copy_control;
-  int reserved[4];
+  /* 1 (ppe_solver 1, IFX_COMPAT_FULL, single GPU): point-Jacobi sweeps run two per pass over memory (kernels_pair.cu:
+   * the intermediate iterate lives in shared memory only, both residuals are evaluated, results and iteration counts
+   * are bit-identical).  Halves the DRAM traffic of the Poisson solve; measured on B200 it is NOT faster than single
+   * sweeps (issue-bound: profiles/r2_pair_kernel.md), hence off by default. */
+  int ppe_pairs;
+  int reserved[3];
 } ifx_options;
 
 /* Per-call statistics (replaces the reference's printf of "iter = %d %f %f", ADSolver.cu:369). */

@@ -165,6 +165,14 @@ def main():
     torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
     dist.init_process_group("nccl")
     ok = True
+    if os.environ.get("IFX_MGPU_QUICK"):      # tools/sanitize.sh: the two cases that touch every slab code path, small
+        ok = run_case(ifx.IFX_COMPAT_REFERENCE, 300, 301, 1, 12) and ok
+        ok = run_bodies_case(300, 161, 1, moving=True) and ok
+        flag = torch.tensor([1 if ok else 0], device="cuda")
+        dist.broadcast(flag, 0)
+        dist.destroy_process_group()
+        print("MGPU_OK" if int(flag.item()) == 1 else "MGPU_FAIL")
+        sys.exit(0 if int(flag.item()) == 1 else 1)
     ok = run_case(ifx.IFX_COMPAT_REFERENCE, 300, 301, 3, 40) and ok
     ok = run_case(ifx.IFX_COMPAT_REFERENCE, 1100, 1200, 2, 24) and ok
     ok = run_case(ifx.IFX_COMPAT_FULL, 260, 130, 3, 40, bc={"u_bc_w": 0.0, "u_bc_e": 0.0, "u_bc_s": 0.0, "u_bc_n": 1.0}) and ok
