@@ -49,6 +49,10 @@ def parse_args():
     ap.add_argument("--ppe-pairs", type=int, default=0,
                     help="1: two Jacobi sweeps per pass over memory in the Poisson solve (ifx_options.ppe_pairs; single GPU; measured "
                          "bit-identical and NOT faster, profiles/r2_pair_kernel.md)")
+    ap.add_argument("--slab-balance", default="rows", choices=["rows", "cost"],
+                    help="more than one GPU: slabs of equal height (default) or of equal estimated cost (rows inside bodies counted as "
+                         "cheaper for the Poisson sweep — measured at 8 GPUs: slower, 20.4 against 19.7 ms per step, the partly solid "
+                         "rows are not cheaper in practice; kept as an experiment switch)")
     ap.add_argument("--no-secondary", action="store_true",
                     help="skip the short runs of BASELINE.json's other configurations (cavity 1024^2, cylinder 4096x2048, converged "
                          "pressure solves) that the default single-GPU run appends under `configs`")
@@ -207,6 +211,31 @@ def bodies_at(nb: int, step: int, dt: float):
         out.append(np.ascontiguousarray(np.stack([cx + ub * dt * step + r * np.cos(th), cy + vb * dt * step + r * np.sin(th)], axis=1)))
         vel.append((ub, vb))
     return out, vel
+
+
+def row_costs(nb: int, ncx: int, ncy: int, dt: float) -> np.ndarray:
+    """Relative cost of every interior row of the workload for the slab partition: the Poisson sweep carries a cell that
+    is not fluid over instead of relaxing it (about a third of the work), the predictor sweep costs the same everywhere.
+    Solid fraction of a row = total chord length of the body polygons (step 0) along the row's cell centres."""
+    b, _ = bodies_at(nb, 0, dt)
+    yc = (np.arange(ncy) + 0.5) / ncy
+    solid = np.zeros(ncy)
+    for m in b:
+        x0, y0 = m[:, 0], m[:, 1]
+        x1, y1 = np.roll(x0, -1), np.roll(y0, -1)
+        lo, hi = np.searchsorted(yc, m[:, 1].min()), np.searchsorted(yc, m[:, 1].max())
+        if hi <= lo:
+            continue
+        Y = yc[lo:hi, None]
+        cross = (y0[None, :] > Y) != (y1[None, :] > Y)
+        dy = np.where(y1 == y0, 1.0, y1 - y0)
+        xi = np.where(cross, x0[None, :] + (Y - y0[None, :]) * ((x1 - x0) / dy)[None, :], np.inf)
+        xi.sort(axis=1)
+        xi = np.where(np.isfinite(xi), xi, 0.0)
+        solid[lo:hi] += np.clip((xi[:, 1::2] - xi[:, 0::2]).sum(axis=1), 0.0, 1.0)
+    s = np.clip(solid, 0.0, 1.0)
+    share_ad, share_ppe, share_rest, c_solid = 0.41, 0.47, 0.12, 0.35       # measured stage shares of the single-GPU step
+    return share_ad + share_rest + share_ppe * (1.0 - s * (1.0 - c_solid))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -575,7 +604,7 @@ def main():
                   "inputs larger than L2, no flush needed" if 8 * 8.0 * (args.nx + 2) * (args.ny + 2) > 4 * 126e6
                   else "NOT larger than L2: an HBM fraction measured on this grid is an L2 figure"),
               "decomposition": f"{world} row slab(s), halo rows by in-kernel NVLink P2P stores, residual sums by P2P mailboxes "
-                               f"(stop decision one sweep behind)"}
+                               f"(stop decision one sweep behind)" + (f", slab heights balanced by {args.slab_balance}" if world > 1 else "")}
 
     if args.impl == "reference":
         if rank != 0:
@@ -606,7 +635,10 @@ def main():
     inp = ifx.make_input(ncx, ncy, args.dt, args.Re, AD_itermax=args.ad_itermax, PPE_itermax=args.ppe_sweeps)
     xf, yf = ifx.uniform_faces(ncx, 1.0), ifx.uniform_faces(ncy, 1.0)
     from immerseflow_b200 import slabs
-    jb, je = slabs.partition_rows(inp.ny, world)[rank]
+    part = slabs.partition_rows(inp.ny, world)
+    if world > 1 and nb > 0 and args.slab_balance == "cost":
+        part = slabs.partition_rows_weighted(inp.ny, world, row_costs(nb, ncx, ncy, args.dt))
+    jb, je = part[rank]
     if args.emulate_slab_of and world == 1:
         jb, je = slabs.partition_rows(inp.ny, args.emulate_slab_of)[0]
     full = args.mode == "full"

@@ -235,6 +235,8 @@ void ifx::make_halo_ctx(ifx_solver* s, int group, int nfields, const int* out_fi
   hx->mseq = ++s->mseq;
   hx->wait_lo = s->sync->flags[group][0];
   hx->wait_hi = s->sync->flags[group][1];
+  hx->gcw_lo = &s->sync->gcflag[0];
+  hx->gcw_hi = &s->sync->gcflag[1];
   if (hx->has_lo) {
     hx->signal_lo = peer_sync(s, r - 1)->flags[group][1];
     for (int f = 0; f < nfields; f++)
@@ -247,7 +249,6 @@ void ifx::make_halo_ctx(ifx_solver* s, int group, int nfields, const int* out_fi
   for (int q = 0; q < s->opt.nranks; q++) {
     XchgSync* ps = peer_sync(s, q);
     hx->mail[q] = &ps->mail[0][0][0];
-    hx->mail_seq[q] = &ps->mail_seq[0][0];
   }
 }
 
@@ -263,7 +264,7 @@ int ifx::halo_wait(ifx_solver* s, int group, unsigned need, int tile_cols) {
 // deliver my first / last owned row of the listed fields to the neighbours and publish `seq` of the group.
 // ctl != null: in-loop use, skipped on the device when the loop finished before iteration `iter`.
 int ifx::halo_push(ifx_solver* s, int group, int nfields, const int* field_index, int tile_cols, unsigned seq,
-                   const LoopCtl* ctl, int iter) {
+                   const LoopCtl* ctl, int iter, bool gc_flags) {
   if (!s->connected || s->opt.nranks == 1) return IFX_OK;
   const int r = s->opt.rank;
   HaloPushArgs a{};
@@ -282,6 +283,10 @@ int ifx::halo_push(ifx_solver* s, int group, int nfields, const int* field_index
   }
   if (a.has_lo) a.signal_lo = peer_sync(s, r - 1)->flags[group][1];
   if (a.has_hi) a.signal_hi = peer_sync(s, r + 1)->flags[group][0];
+  if (gc_flags) {
+    if (a.has_lo) a.gc_signal_lo = &peer_sync(s, r - 1)->gcflag[1];
+    if (a.has_hi) a.gc_signal_hi = &peer_sync(s, r + 1)->gcflag[0];
+  }
   s->launches++;
   IFX_CUDA(s, launch_halo_push(a, s->stream));
   return IFX_OK;
@@ -289,10 +294,10 @@ int ifx::halo_push(ifx_solver* s, int group, int nfields, const int* field_index
 
 // push + wait for the neighbours' rows.  With nfields == 0 this is a pairwise barrier: everything a neighbour
 // enqueued before its call is complete when the wait kernel lets this stream continue.
-int ifx::halo_exchange(ifx_solver* s, int group, int nfields, const int* field_index, int tile_cols) {
+int ifx::halo_exchange(ifx_solver* s, int group, int nfields, const int* field_index, int tile_cols, bool gc_flags) {
   if (!s->connected || s->opt.nranks == 1) return IFX_OK;
   const unsigned seq = ++s->seq[group];
-  int rc = halo_push(s, group, nfields, field_index, tile_cols, seq, nullptr, 0);
+  int rc = halo_push(s, group, nfields, field_index, tile_cols, seq, nullptr, 0, gc_flags);
   if (rc != IFX_OK) return rc;
   return halo_wait(s, group, seq, tile_cols);
 }
@@ -718,7 +723,7 @@ int ifx::run_ad_loop(ifx_solver* s, ifx_step_stats* st, bool full) {
   const int tw_ad = v4_tile_cols(2);
   if (slabs) {   // halo rows of the starting field (also what the source pass reads)
     const int fi[2] = {base, 2 + base};
-    if ((rc = halo_exchange(s, 0, 2, fi, tw_ad)) != IFX_OK) return rc;
+    if ((rc = halo_exchange(s, 0, 2, fi, tw_ad, full && bodies_on_slabs(s))) != IFX_OK) return rc;
   }
 
   // ---- velf + BC + ADSource (ADSolver.cu:298-311) in one pass
@@ -768,8 +773,10 @@ int ifx::run_ad_loop(ifx_solver* s, ifx_step_stats* st, bool full) {
   bool lag_first = true;
   const int no_exchange = std::getenv("IFX_EXP_NO_RESIDUAL_EXCHANGE") ? 1 : 0;     // timing diagnostic only
   unsigned seq_before = s->seq[0];
-  // ghost cells on slabs: sweep -> ghost-cell kernel (reads the neighbours' previous iterate) -> push kernel, which
-  // re-delivers the boundary rows (now with their ghost cells) and only then publishes the sweep's sequence number
+  // ghost cells on slabs: sweep (delivers its boundary rows, ghost cells with throw-away values) -> ghost-cell kernel
+  // (reads the neighbours' previous iterate over NVLink, closes the ghost cells — also those in the rows the sweep
+  // delivered — and publishes the neighbours' gcflag).  Two launches per iteration; the next sweep's boundary tiles wait
+  // for both the tile flags and the gcflag (HaloCtx.defer)
   const bool defer = full && bodies_on_slabs(s);
   if (defer && ry < IFX_GC_REACH) return fail(s, IFX_ERR_INVALID, "IFX_ROWS_PER_CTA must be >= 4 with bodies on slabs");
 
@@ -794,16 +801,29 @@ int ifx::run_ad_loop(ifx_solver* s, ifx_step_stats* st, bool full) {
       set_iter(++m);
       ja.force = 0;
       if ((rc = launch_ad_jacobi(s, ja, grid, exact)) != IFX_OK) return rc;
-      if (full && s->has_gc) {   // ghost cells of iterate m from iterate m-1 (Jacobi-lagged, like every other cell)
+      if (full && (s->has_gc || defer)) {   // ghost cells of iterate m from iterate m-1 (Jacobi-lagged, like every other cell)
         s->launches++;
-        const int src = (base + m - 1) & 1;
+        const int src = (base + m - 1) & 1, dst = src ^ 1;
+        GcPush gp{};
+        if (defer) {
+          const int r = s->opt.rank;
+          gp.active = 1;
+          gp.has_lo = r > 0; gp.has_hi = r < s->opt.nranks - 1;
+          gp.pitch = L.pitch;
+          gp.row_lo = (L.jb - L.j0) * L.pitch; gp.row_hi = (L.je - 1 - L.j0) * L.pitch;
+          const int fo[2] = {dst, 2 + dst};
+          for (int f = 0; f < 2; f++) {
+            if (gp.has_lo) gp.dst_lo[f] = peer_field(s, r - 1, fo[f]) + (size_t)(s->peer_nyl[r - 1] - 1) * L.pitch;
+            if (gp.has_hi) gp.dst_hi[f] = peer_field(s, r + 1, fo[f]);
+          }
+          if (gp.has_lo) gp.signal_lo = &peer_sync(s, r - 1)->gcflag[1];
+          if (gp.has_hi) gp.signal_hi = &peer_sync(s, r + 1)->gcflag[0];
+          gp.seq = ja.hx.seq;
+          gp.ticket = reinterpret_cast<unsigned*>(s->d_counters + 2);
+        }
         IFX_CUDA(s, launch_gc_velocity(s->gc.count, s->gc.cell, s->gc.stencil, s->gc.w_dir, s->gc.body, s->d_ub, s->d_vb,
-                                       ja.uC, ja.vC, gc_peers(s, src, 2 + src), ja.uT, ja.vT, 0, s->ctl, m, s->stream));
-      }
-      if (defer) {
-        const int dst = (base + m) & 1;
-        const int fo[2] = {dst, 2 + dst};
-        if ((rc = halo_push(s, 0, 2, fo, tw_ad, ja.hx.seq, s->ctl, m)) != IFX_OK) return rc;
+                                       ja.uC, ja.vC, gc_peers(s, src, 2 + src), ja.uT, ja.vT, 0, s->ctl, m, s->stream,
+                                       defer ? &gp : nullptr));
       }
       if (exact && (rc = exact_decide(s, ja.rc, true)) != IFX_OK) return rc;
     }

@@ -103,15 +103,24 @@ struct LoopCtl {
 
 struct XchgSync {
   unsigned flags[IFX_SYNC_GROUPS][2][IFX_MAX_TILES];      // [group][0: written by lower nbr, 1: by upper][tile]
-  double mail[IFX_MAIL_SLOTS][IFX_MAX_RANKS][IFX_MAIL_VALS];   // per-rank residual partials of one launch
-  unsigned mail_seq[IFX_MAIL_SLOTS][IFX_MAX_RANKS];
+  unsigned gcflag[2];                                     // predictor with bodies: the neighbour's ghost-cell kernel of
+                                                          // iteration seq is through ([0]: lower neighbour, [1]: upper)
+  // per-rank residual partials of one launch, as self-validating 8-byte packets {32 data bits, 32-bit launch tag}: two
+  // packets per double, no fence and no separate flag (the layout of NCCL's LL protocol)
+  unsigned long long mail[IFX_MAIL_SLOTS][IFX_MAX_RANKS][2 * IFX_MAIL_VALS];
 };
 
 struct HaloCtx {
   int nranks, rank;
   int has_lo, has_hi;              // a neighbour slab below / above
   unsigned seq;                    // sequence number of this launch within its sync group
-  int defer;                       // 1: a later kernel publishes this launch's sequence number (ghost cells on slabs)
+  int defer;                       // 1: predictor with immersed bodies on slabs.  The ghost cells of an iterate are closed by
+                                   // a kernel of their own (kernels_ib.cu) that reads the neighbours' previous iterate over
+                                   // NVLink, overwrites the ghost cells in the rows this launch delivered and then publishes
+                                   // gcflag: halo rows are complete, and rows near a slab boundary may be overwritten, only
+                                   // after the neighbours' gcflag of the previous iteration
+  const unsigned* gcw_lo;          // my gcflag[0] / gcflag[1] (written by the lower / upper neighbour)
+  const unsigned* gcw_hi;
   unsigned mseq;                   // global sweep counter (mailbox slot / tag)
   const unsigned* wait_lo;         // my flags written by the lower neighbour, per tile
   const unsigned* wait_hi;
@@ -119,8 +128,7 @@ struct HaloCtx {
   unsigned* signal_hi;
   double* peer_row_lo[2];          // lower neighbour's top halo row of the OUTPUT buffer (per field), row start
   double* peer_row_hi[2];          // upper neighbour's bottom halo row
-  double* mail[IFX_MAX_RANKS];     // every rank's mail[][][] (mine included)
-  unsigned* mail_seq[IFX_MAX_RANKS];
+  unsigned long long* mail[IFX_MAX_RANKS];   // every rank's mail[][][] (mine included)
 };
 
 #ifndef IFX_HOST_SHIM
@@ -139,6 +147,14 @@ __device__ __forceinline__ unsigned ld_relaxed_sys(const unsigned* p) {
 }
 __device__ __forceinline__ void st_relaxed_sys(unsigned* p, unsigned v) {
   asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 __device__ __forceinline__ void wait_seq_ge(const unsigned* p, unsigned need) {
   // sequence numbers wrap after 2^32 launches; compare as a signed distance

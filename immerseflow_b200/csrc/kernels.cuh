@@ -86,31 +86,47 @@ struct PpeSweepArgs {
 // iterates) and says so itself: {a0, b0, a1, b1, number of pairs, iterate index of the first pair}.
 static __device__ __noinline__ void slab_post_partial(const HaloCtx& hx, unsigned tag, const double* v, int npairs,
                                                       int eval_first) {
+  // Fire and forget: every 8-byte packet carries 32 bits of data and the launch tag, so the reader needs neither a flag
+  // nor a fence — and the one thread that runs at the tail of every launch does not sit out an NVLink round trip
+  // (measured at 8 GPUs: the fenced data-then-flag version cost 9 us per launch, 3.5 % of the step).
   const unsigned slot = tag & (IFX_MAIL_SLOTS - 1);
   const unsigned me = (unsigned)hx.rank;
+  const double w[IFX_MAIL_VALS] = {v[0], v[1], v[2], v[3], (double)npairs, (double)eval_first};
   for (int r = 0; r < hx.nranks; ++r) {
-    double* m = hx.mail[r] + ((size_t)slot * IFX_MAX_RANKS + me) * IFX_MAIL_VALS;
-    m[0] = v[0]; m[1] = v[1]; m[2] = v[2]; m[3] = v[3]; m[4] = (double)npairs; m[5] = (double)eval_first;
+    unsigned long long* m = hx.mail[r] + ((size_t)slot * IFX_MAX_RANKS + me) * (2 * IFX_MAIL_VALS);
+#pragma unroll
+    for (int q = 0; q < IFX_MAIL_VALS; ++q) {
+      const unsigned long long bits = (unsigned long long)__double_as_longlong(w[q]);
+      st_relaxed_sys_u64(m + 2 * q, ((unsigned long long)tag << 32) | (bits & 0xffffffffull));
+      st_relaxed_sys_u64(m + 2 * q + 1, ((unsigned long long)tag << 32) | (bits >> 32));
+    }
   }
-  // message passing: data, ONE system-scope fence, then the tags as relaxed stores (a release store per rank would
-  // pay the NVLink round trip eight times over, at the tail of every launch, with one thread of one CTA running)
-  __threadfence_system();
-  for (int r = 0; r < hx.nranks; ++r) st_relaxed_sys(hx.mail_seq[r] + slot * IFX_MAX_RANKS + me, tag);
 }
 static __device__ __noinline__ void slab_collect_partials(const HaloCtx& hx, unsigned tag, double* v, int& npairs,
                                                           int& eval_first) {
   const unsigned slot = tag & (IFX_MAIL_SLOTS - 1);
   const unsigned me = (unsigned)hx.rank;
-  for (int r = 0; r < hx.nranks; ++r) {      // all tags (relaxed polls), ONE fence, then the data
-    const unsigned* q = hx.mail_seq[me] + slot * IFX_MAX_RANKS + r;
-    while (ld_relaxed_sys(q) != tag) { __nanosleep(32); }
-  }
-  __threadfence_system();
   double g[4] = {0.0, 0.0, 0.0, 0.0};
   for (int r = 0; r < hx.nranks; ++r) {      // rank order: same operands, same order, same sums on every rank
-    const volatile double* m = hx.mail[me] + ((size_t)slot * IFX_MAX_RANKS + r) * IFX_MAIL_VALS;
-    g[0] += m[0]; g[1] += m[1]; g[2] += m[2]; g[3] += m[3];
-    if (r == 0) { npairs = (int)m[4]; eval_first = (int)m[5]; }
+    const unsigned long long* m = hx.mail[me] + ((size_t)slot * IFX_MAX_RANKS + r) * (2 * IFX_MAIL_VALS);
+    // all twelve packets of a rank are loaded back to back (independent loads: one L2 round trip, not twelve) and
+    // re-read together until every one carries the tag — with a lagged decision they arrived a sweep ago
+    unsigned long long pk[2 * IFX_MAIL_VALS];
+    bool all;
+    do {
+#pragma unroll
+      for (int q = 0; q < 2 * IFX_MAIL_VALS; ++q) pk[q] = ld_relaxed_sys_u64(m + q);
+      all = true;
+#pragma unroll
+      for (int q = 0; q < 2 * IFX_MAIL_VALS; ++q) all = all && ((pk[q] >> 32) == tag);
+      if (!all) __nanosleep(64);
+    } while (!all);
+    double w[IFX_MAIL_VALS];
+#pragma unroll
+    for (int q = 0; q < IFX_MAIL_VALS; ++q)
+      w[q] = __longlong_as_double((long long)((pk[2 * q + 1] << 32) | (pk[2 * q] & 0xffffffffull)));
+    g[0] += w[0]; g[1] += w[1]; g[2] += w[2]; g[3] += w[3];
+    if (r == 0) { npairs = (int)w[4]; eval_first = (int)w[5]; }
   }
   v[0] = g[0]; v[1] = g[1]; v[2] = g[2]; v[3] = g[3];
 }
@@ -284,10 +300,24 @@ cudaError_t launch_gc_build(const Layout& L, const double* xc, const double* yc,
                             const uint8_t* celltype, const int* rowstart, int ngc, int* cell, int* ref_id,
                             int* body, int* stencil, int* stencil_ref, double* wd, double* wn, double* bi, double* ip,
                             int* err, cudaStream_t st);
+// in-loop ghost-cell kernel of a slab run (HaloCtx.defer): besides closing its ghost cells it overwrites those that lie
+// in the slab's first / last owned row in the neighbours' halo rows (the sweep delivered throw-away values there) and,
+// when the whole grid is through, publishes the neighbours' gcflag
+struct GcPush {
+  int active;
+  int has_lo, has_hi;
+  int row_lo, row_hi;              // padded offset of the start of my first / last owned row (lidx(L, 0, jl) - IFX_PADL)
+  int pitch;
+  double* dst_lo[2];               // lower neighbour's top halo row start (u, v); upper neighbour's bottom halo row start
+  double* dst_hi[2];
+  unsigned* signal_lo; unsigned* signal_hi;
+  unsigned seq;
+  unsigned* ticket;
+};
 cudaError_t launch_gc_velocity(int ngc, const int* cell, const int* stencil, const double* wd, const int* body,
                                const double* ub, const double* vb, const double* usrc, const double* vsrc,
                                const GcPeers& pr, double* udst, double* vdst, int gather, const LoopCtl* ctl, int iter,
-                               cudaStream_t st);
+                               cudaStream_t st, const GcPush* push = nullptr);
 cudaError_t launch_gc_pressure(int ngc, const int* cell, const int* stencil, const double* wn, const double* psrc,
                                const GcPeers& pr, double* pdst, int gather, cudaStream_t st);
 cudaError_t launch_gc_scatter(int ngc, const int* cell, const double* a, double* qa, const double* b, double* qb,
@@ -302,6 +332,7 @@ struct HaloPushArgs {
   int has_lo, has_hi;
   unsigned seq;
   unsigned* signal_lo; unsigned* signal_hi;
+  unsigned* gc_signal_lo; unsigned* gc_signal_hi;   // also publish the neighbours' gcflag (start of a predictor loop) or null
   int tile_cols, ntiles;
   const LoopCtl* ctl;              // in-loop use: skip when the loop finished before iteration `iter` (else null)
   int iter;

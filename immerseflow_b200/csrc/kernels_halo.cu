@@ -28,6 +28,10 @@ static __global__ void k_halo_push(HaloPushArgs a) {
   if (threadIdx.x == 0) {
     if (a.has_lo) st_release_sys(a.signal_lo + b, a.seq);
     if (a.has_hi) st_release_sys(a.signal_hi + b, a.seq);
+    if (b == 0) {      // start of a predictor loop with bodies: nothing of the neighbours' is being read by a ghost-cell kernel
+      if (a.has_lo && a.gc_signal_lo) st_release_sys(a.gc_signal_lo, a.seq);
+      if (a.has_hi && a.gc_signal_hi) st_release_sys(a.gc_signal_hi, a.seq);
+    }
   }
 }
 

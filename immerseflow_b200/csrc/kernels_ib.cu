@@ -394,15 +394,34 @@ static __global__ void k_gc_velocity(int ngc, const int* __restrict__ cell, cons
                                      const double* __restrict__ ub, const double* __restrict__ vb,
                                      const double* __restrict__ usrc, const double* __restrict__ vsrc, GcPeers pr,
                                      double* __restrict__ udst, double* __restrict__ vdst, int gather,
-                                     const LoopCtl* ctl, int iter) {
+                                     const LoopCtl* ctl, int iter, GcPush ps) {
   // in-loop use: iteration `iter` ran iff the loop was not already finished by an earlier iteration
   if (ctl && ctl->done && ctl->iter < iter) return;
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= ngc) return;
-  const double pu = gc_dirichlet(usrc, pr.lo[0], pr.hi[0], stencil + 4 * g, wd + 5 * g, ub[body[g]]);
-  const double pv = gc_dirichlet(vsrc, pr.lo[1], pr.hi[1], stencil + 4 * g, wd + 5 * g, vb[body[g]]);
-  const int o = gather ? g : cell[g];
-  udst[o] = pu; vdst[o] = pv;
+  if (g < ngc) {
+    const double pu = gc_dirichlet(usrc, pr.lo[0], pr.hi[0], stencil + 4 * g, wd + 5 * g, ub[body[g]]);
+    const double pv = gc_dirichlet(vsrc, pr.lo[1], pr.hi[1], stencil + 4 * g, wd + 5 * g, vb[body[g]]);
+    const int o = gather ? g : cell[g];
+    udst[o] = pu; vdst[o] = pv;
+    if (ps.active) {      // a ghost cell of my first / last owned row also lives in the neighbour's halo row
+      if (ps.has_lo && o >= ps.row_lo && o < ps.row_lo + ps.pitch) { ps.dst_lo[0][o - ps.row_lo] = pu; ps.dst_lo[1][o - ps.row_lo] = pv; }
+      if (ps.has_hi && o >= ps.row_hi && o < ps.row_hi + ps.pitch) { ps.dst_hi[0][o - ps.row_hi] = pu; ps.dst_hi[1][o - ps.row_hi] = pv; }
+    }
+  }
+  if (!ps.active) return;
+  // the whole grid is through (ticket): my remote reads of the neighbours' previous iterate are over and the halo rows
+  // I feed are complete — tell both neighbours
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned t = atomicAdd(ps.ticket, 1u);
+    if (t == gridDim.x - 1) {
+      *ps.ticket = 0u;
+      __threadfence_system();
+      if (ps.has_lo) st_release_sys(ps.signal_lo, ps.seq);
+      if (ps.has_hi) st_release_sys(ps.signal_hi, ps.seq);
+    }
+  }
 }
 
 static __global__ void k_gc_pressure(int ngc, const int* __restrict__ cell, const int* __restrict__ stencil,
@@ -455,10 +474,12 @@ cudaError_t launch_gc_build(const Layout& L, const double* xc, const double* yc,
 cudaError_t launch_gc_velocity(int ngc, const int* cell, const int* stencil, const double* wd, const int* body,
                                const double* ub, const double* vb, const double* usrc, const double* vsrc,
                                const GcPeers& pr, double* udst, double* vdst, int gather, const LoopCtl* ctl, int iter,
-                               cudaStream_t st) {
-  if (ngc <= 0) return cudaSuccess;
-  k_gc_velocity<<<(ngc + 127) / 128, 128, 0, st>>>(ngc, cell, stencil, wd, body, ub, vb, usrc, vsrc, pr, udst, vdst, gather,
-                                                   ctl, iter);
+                               cudaStream_t st, const GcPush* push) {
+  GcPush ps{};
+  if (push) ps = *push;
+  if (ngc <= 0 && !ps.active) return cudaSuccess;        // (a slab without ghost cells still has its flag to publish)
+  const int nblk = ngc > 0 ? (ngc + 127) / 128 : 1;
+  k_gc_velocity<<<nblk, 128, 0, st>>>(ngc, cell, stencil, wd, body, ub, vb, usrc, vsrc, pr, udst, vdst, gather, ctl, iter, ps);
   return cudaGetLastError();
 }
 

@@ -132,9 +132,9 @@ int full_refresh_velocity_bc(ifx_solver* s, int buf);
 int full_refresh_pressure_bc(ifx_solver* s, int buf);
 // slabs
 void make_halo_ctx(ifx_solver* s, int group, int nfields, const int* out_field_index, HaloCtx* hx);
-int halo_exchange(ifx_solver* s, int group, int nfields, const int* field_index, int tile_cols);
+int halo_exchange(ifx_solver* s, int group, int nfields, const int* field_index, int tile_cols, bool gc_flags = false);
 int halo_push(ifx_solver* s, int group, int nfields, const int* field_index, int tile_cols, unsigned seq,
-              const LoopCtl* ctl, int iter);
+              const LoopCtl* ctl, int iter, bool gc_flags = false);
 bool bodies_on_slabs(const ifx_solver* s);
 GcPeers gc_peers(ifx_solver* s, int f0, int f1);
 int halo_wait(ifx_solver* s, int group, unsigned need, int tile_cols);

@@ -32,6 +32,39 @@ def partition_rows(ny: int, nranks: int) -> List[Tuple[int, int]]:
     return out
 
 
+def partition_rows_weighted(ny: int, nranks: int, row_cost: Sequence[float], min_rows: int = 8) -> List[Tuple[int, int]]:
+    """Contiguous slabs of (nearly) equal COST instead of equal height: `row_cost[k]` is the relative cost of interior row
+    k + 1 (k = 0 .. ny-3).  Rows inside immersed bodies are cheaper for the Poisson sweep (a cell that is not fluid is
+    carried over, not relaxed), so equal-height slabs leave the ranks without a body as the slowest ones and every sweep
+    runs at their pace.  Any contiguous partition gives bit-identical results (tests/test_gpu_slabs.py runs uneven
+    slabs); every slab gets at least `min_rows` rows (ghost-cell stencils reach 4 rows into a neighbour)."""
+    n = ny - 2
+    if nranks < 1 or nranks > 8:
+        raise ValueError("1..8 slabs")
+    if len(row_cost) != n:
+        raise ValueError("one cost per interior row")
+    if n < nranks * min_rows:
+        return partition_rows(ny, nranks)
+    total = float(sum(row_cost))
+    if not total > 0.0:
+        return partition_rows(ny, nranks)
+    out, j, acc, k = [], 1, 0.0, 0
+    for r in range(nranks):
+        target = total * (r + 1) / nranks
+        j0 = j
+        last_possible = ny - 1 - (nranks - 1 - r) * min_rows           # leave min_rows for every slab still to come
+        while j < last_possible and (j - j0 < min_rows or acc + 0.5 * row_cost[k] < target):
+            acc += row_cost[k]
+            j += 1
+            k += 1
+        if r == nranks - 1:
+            while j < ny - 1:
+                acc += row_cost[k]; j += 1; k += 1
+        out.append((j0, j))
+    assert j == ny - 1 and all(e - b >= min_rows for b, e in out)
+    return out
+
+
 def local_rows(ny: int, nranks: int, rank: int) -> Tuple[int, int]:
     """Stored global rows [lo, hi) of a rank: its owned rows plus one halo / ghost row on each side."""
     jb, je = partition_rows(ny, nranks)[rank]

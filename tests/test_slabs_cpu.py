@@ -73,3 +73,22 @@ def test_blob_allgather_gloo_world2(tmp_path):
                        capture_output=True, text=True, timeout=300, env=env)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert r.stdout.count("ok") == 2
+
+
+def test_weighted_partition_balances_cost_and_keeps_every_slab_tall_enough():
+    import numpy as np
+    ny = 1026
+    w = np.ones(ny - 2)
+    w[100:400] = 0.6            # rows through a body: cheaper
+    for n in (1, 2, 3, 4, 8):
+        part = slabs.partition_rows_weighted(ny, n, w)
+        assert part[0][0] == 1 and part[-1][1] == ny - 1
+        assert all(a[1] == b[0] for a, b in zip(part, part[1:]))
+        assert all(e - b >= 8 for b, e in part)
+        costs = [w[b - 1:e - 1].sum() for b, e in part]
+        assert max(costs) - min(costs) <= 2.0 + 1e-9, costs          # within a couple of rows of each other
+    # equal costs -> the equal-height partition (up to a row)
+    eq, pw = slabs.partition_rows(ny, 4), slabs.partition_rows_weighted(ny, 4, np.ones(ny - 2))
+    assert all(abs((e1 - b1) - (e2 - b2)) <= 1 for (b1, e1), (b2, e2) in zip(eq, pw))
+    # too few rows for the minimum height: falls back to equal heights
+    assert slabs.partition_rows_weighted(20, 4, np.ones(18)) == slabs.partition_rows(20, 4)

@@ -7,14 +7,20 @@
 # (mbarrier ring); synccheck: barrier misuse.  Logs: gpurun_out/sanitizer_*.log (copied to profiles/ by hand).
 mkdir -p gpurun_out
 if [ "$1" = "slabs" ]; then
+  # every rank runs under its own sanitizer (no launcher in between, so the tool certainly sees the worker's kernels)
   for tool in memcheck racecheck; do
-    echo "== compute-sanitizer --tool $tool, 2 ranks (tests/mgpu_worker.py, IFX_MGPU_QUICK=1)"
-    IFX_MGPU_QUICK=1 timeout 420 compute-sanitizer --tool $tool --target-processes all --error-exitcode 9 \
-      --log-file gpurun_out/sanitizer_slabs_${tool}.%p.log \
-      python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29541 tests/mgpu_worker.py \
-      > gpurun_out/sanitizer_slabs_${tool}_run.log 2>&1
-    echo "exit $?"; tail -2 gpurun_out/sanitizer_slabs_${tool}_run.log
-    grep -h "ERROR SUMMARY" gpurun_out/sanitizer_slabs_${tool}.*.log | sort | uniq -c
+    echo "== compute-sanitizer --tool $tool, 2 ranks (tests/mgpu_worker.py, IFX_MGPU_QUICK=1), one sanitizer per rank"
+    for r in 0 1; do
+      IFX_MGPU_QUICK=1 RANK=$r LOCAL_RANK=$r WORLD_SIZE=2 MASTER_ADDR=127.0.0.1 MASTER_PORT=29541 \
+        timeout 420 compute-sanitizer --tool $tool --error-exitcode 9 --log-file gpurun_out/sanitizer_slabs_${tool}_rank$r.log \
+        python tests/mgpu_worker.py > gpurun_out/sanitizer_slabs_${tool}_rank${r}_run.log 2>&1 &
+    done
+    wait
+    for r in 0 1; do
+      tail -1 gpurun_out/sanitizer_slabs_${tool}_rank${r}_run.log
+      grep -h "SUMMARY" gpurun_out/sanitizer_slabs_${tool}_rank$r.log
+      grep -c "k_sweep_v4\|k_halo\|k_gc" gpurun_out/sanitizer_slabs_${tool}_rank$r.log
+    done
   done
   exit 0
 fi
