@@ -226,7 +226,7 @@ class ImmerseFlow:
                  rank: int = 0, nranks: int = 1, j_begin: int = 0, j_end: int = 0,
                  sweeps_per_batch: int = 64, ppe_abs_residual: int = 0,
                  ad_tol: Optional[float] = None, ppe_tol: Optional[float] = None,
-                 ppe_solver: int = 0, ppe_omega: float = 0.0, zero_copy_control: int = 0, use_graphs: int = 0,
+                 ppe_solver: int = 0, ppe_omega: float = 0.0, zero_copy_control: int = 0, use_graphs: Optional[int] = None,
                  ppe_pairs: int = 0):
         self.lib = load_library()
         self.Input = inp
@@ -243,7 +243,8 @@ class ImmerseFlow:
         opt.ppe_solver, opt.ppe_omega = ppe_solver, ppe_omega      # 2 line SOR, 3 red-black SOR, 4 / 5 multigrid (full mode)
         opt.zero_copy_control = zero_copy_control
         opt.ppe_pairs = ppe_pairs                                  # two Jacobi sweeps per pass (opt-in, see immerseflow_c.h)
-        opt.use_graphs = use_graphs
+        if use_graphs is not None:                                 # library default: on
+            opt.use_graphs = use_graphs
         if ad_tol is not None:
             opt.ad_tol = ad_tol
         if ppe_tol is not None:
