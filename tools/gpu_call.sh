@@ -1,21 +1,18 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_slabs.py -q -m gpu -p no:cacheprovider -x 2>&1 | tail -3 | tee gpurun_out/r2_slabs_tests8.log
-run() { # name, nproc, extra args
-  timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $2 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus $2 --steps 6 --warmup 3 --no-cpu-baseline --no-e2e --no-ref-cuda --no-secondary $3 > gpurun_out/r2_scale_$1.json 2> gpurun_out/r2_scale_$1.err
-  python - <<PY
+timeout 1200 python -m pytest tests -q -m gpu -p no:cacheprovider 2>&1 | tail -6 | tee gpurun_out/r2_tests_final.log
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+( time timeout 900 python bench.py > gpurun_out/r2_bench_final.json 2> gpurun_out/r2_bench_final.err ) 2>&1 | grep real
+python - <<'PY'
 import json
-try:
-    t=open('gpurun_out/r2_scale_$1.json').read()
-    d=json.loads(t[t.index('{'):])
-    r=d['roofline']
-    print('$1', round(d['value']), 'ms/step', round(d['ms_per_step'],2), 'dev', round(d['device_ms_per_step'],2), 'ad/launch', round(r['predictor']['ms_per_launch'],4), 'ppe/launch', round(r['ms_per_launch'],4), 'proj', round(r['projection_ms'],3), 'ib', round(r['iblank_ghost_cells_ms'],3), d['clocks']['sm_mhz'], d['clocks']['reasons'], d['gpu_launches'], 'parity', (d.get('parity_check') or {}).get('bit_exact'), d.get('slab_parity'))
-except Exception as e:
-    print('$1', e); print(open('gpurun_out/r2_scale_$1.err').read()[-800:])
+t=open('gpurun_out/r2_bench_final.json').read(); d=json.loads(t[t.index('{'):])
+print(d['value'], d['ms_per_step'], 'e2e', d['e2e']['value'], 'parity', d['parity_check']['bit_exact'], 'refcuda', d['ref_cuda_baseline'].get('value'), 'cpu', d['cpu_baseline']['value'], 'frac', d['roofline']['frac'], d['roofline']['predictor']['frac'])
+for c in d.get('configs', []):
+    print({k: c.get(k) for k in ('name','error','ms_per_step','value','poisson_iterations','poisson_converged','gpu_launches_per_step')})
 PY
-}
-run n8 8 ""
-run n8_rows 8 "--slab-balance rows --no-parity-check"
-run n4 4 ""
-run n2 2 ""
-run n1 1 ""
+tail -2 gpurun_out/r2_bench_final.err
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r2_launches.csv python bench.py --no-cpu-baseline --no-e2e --no-parity-check --no-ref-cuda --no-secondary --steps 1 --warmup 1 > gpurun_out/r2_launches_run.log 2>&1
+wc -l gpurun_out/r2_launches.csv
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_sweep_v4 --launch-skip 30 --launch-count 1 -f -o gpurun_out/r2_final_ppe python bench.py --no-cpu-baseline --no-e2e --no-parity-check --no-ref-cuda --no-secondary --steps 1 --warmup 1 > gpurun_out/r2_final_ncu1.log 2>&1
+timeout 600 ncu --set full --clock-control none -k regex:k_sweep_v4 --launch-skip 10 --launch-count 1 -f -o gpurun_out/r2_final_ad python bench.py --no-cpu-baseline --no-e2e --no-parity-check --no-ref-cuda --no-secondary --steps 1 --warmup 1 > gpurun_out/r2_final_ncu2.log 2>&1
+ls -la gpurun_out/*.ncu-rep | tail -3
