@@ -771,7 +771,7 @@ int ifx::run_ad_loop(ifx_solver* s, ifx_step_stats* st, bool full) {
   // step refreshes anyway, whereas the reference-compatible step reads that ring as the reference left it (App. A Q5).
   const bool lag = slabs && full;
   bool lag_first = true;
-  const int no_exchange = std::getenv("IFX_EXP_NO_RESIDUAL_EXCHANGE") ? 1 : 0;     // timing diagnostic only
+  const int no_exchange = 0;
   unsigned seq_before = s->seq[0];
   // ghost cells on slabs: sweep (delivers its boundary rows, ghost cells with throw-away values) -> ghost-cell kernel
   // (reads the neighbours' previous iterate over NVLink, closes the ghost cells — also those in the rows the sweep
@@ -958,7 +958,7 @@ int ifx::run_ppe_loop(ifx_solver* s, ifx_step_stats* st, bool laplace_ref) {
     const int np = s->np;
     const bool lag = slabs && !sor;
     bool lag_first = true;
-    const int no_exchange = std::getenv("IFX_EXP_NO_RESIDUAL_EXCHANGE") ? 1 : 0;   // timing diagnostic only
+    const int no_exchange = 0;      // (1 only for the forced re-creation sweeps below: nothing to decide, nothing to exchange)
     const int partner = (base + 1) % np;      // SOR: the other buffer of the pair
     auto set_sweep = [&](int m) {     // sweep m: iterate m-1 -> iterate m, evaluates residual(iterate m-1)
       const int src = sor ? base : (base + m - 1) % np;

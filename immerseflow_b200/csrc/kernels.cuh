@@ -19,7 +19,7 @@ struct ReduceCfg {
   int lag;          // slabs: post this launch's partials, decide on the PREVIOUS launch's (no cross-GPU wait on the
                     // critical path); the loop's last launch is decided by a flush kernel (launch_lag_flush)
   int lag_first;    // lag: first launch of the loop or after a flush — nothing to decide yet
-  int no_exchange;  // diagnostic (IFX_EXP_NO_RESIDUAL_EXCHANGE): every rank decides on its own sum — timing only
+  int no_exchange;  // slabs: this launch takes part in no residual exchange (forced re-creation of an iterate: no decision)
   double tol;
   double band;      // relative half-width of the rounding band (times the abs-sum)
 };
