@@ -34,6 +34,7 @@ SOURCES = [
     ("kernels_pair.cu", True),
     ("kernels_reduce.cu", True),
     ("kernels_misc.cu", True),
+    ("kernels_facemask.cu", True),
     ("kernels_halo.cu", True),
     ("kernels_full.cu", True),
     ("kernels_ib.cu", True),

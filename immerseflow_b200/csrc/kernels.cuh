@@ -1,6 +1,7 @@
 // kernels.cuh — kernel argument blocks, launch geometry and the fused residual reduction.
 #pragma once
 #include "common.cuh"
+#include "facemask.cuh"
 
 namespace ifx {
 
@@ -349,15 +350,7 @@ cudaError_t launch_decide_exact(LoopCtl* ctl, const double* sums, const ReduceCf
 cudaError_t launch_init_vortex(const Layout& L, const double* xc, const double* yc, double* u, double* v, double* p,
                                cudaStream_t st);
 cudaError_t launch_fill_u8(uint8_t* p, size_t n, uint8_t v, cudaStream_t st);
-cudaError_t launch_build_facemask(const Layout& L, const uint8_t* celltype, uint8_t* facemask, int jl_lo, int jl_hi,
-                                  cudaStream_t st);
-// face-mask bits of the general Poisson operator (kernels_misc.cu: k_build_facemask)
-#define IFX_FM_W 1u
-#define IFX_FM_E 2u
-#define IFX_FM_S 4u
-#define IFX_FM_N 8u
-#define IFX_FM_FLUID 16u
-#define IFX_FM_PLAIN 0x1fu
+// (face masks: facemask.cuh)
 cudaError_t launch_copy_words(void* dst, const void* src, size_t bytes, cudaStream_t st);   // bytes: multiple of 4
 cudaError_t launch_pack_u8(const Layout& L, const uint8_t* padded, double* dense, int raw, cudaStream_t st);
 
