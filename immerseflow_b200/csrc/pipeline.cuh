@@ -4,6 +4,12 @@
 // of bytes in flight per SM is set by the ring depth, not by registers or occupancy — which is what a
 // 6.5 TB/s x ~0.7 us memory system needs (~30 KB per SM in flight) and what the register-rolled v1
 // kernels could not provide (ncu: 45 % / 28 % of DRAM peak at 12 / 20 resident warps).
+//
+// Two proxies meet in a stage.  Filled -> consumed: the bulk copy's complete_tx on the stage's "full" barrier makes its
+// (async-proxy) writes visible to whoever observes the phase — nothing to add.  Consumed -> refilled: the consumers' arrive
+// on the "empty" barrier does NOT order their (generic-proxy) loads before the refill; an LDS that has only been issued
+// can be overtaken by the copy.  So a consumer arrives only after the values it loaded have been USED (here: after the
+// row's stores, which depend on them), or after fence.proxy.async.  profiles/r2_nc2_race.md has the measurement.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
