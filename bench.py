@@ -804,6 +804,10 @@ def main():
                               "share_of_step": ad_share},
                 "projection_ms": float(np.mean(cor_ms)), "iblank_ghost_cells_ms": float(np.mean(ib_ms)),
                 "ghost_cells": int(s.lib.ifx_ghost_cell_count(s._h))}
+    if full and world == 1 and roofline["traffic"] is not None:
+        roofline["traffic_note"] = ("ncu capture of the kernel's two-columns-per-thread geometry (256-column tiles, what slabs run); a "
+                                    "single GPU runs the four-column geometry since the end of round 2: 516 instead of 2 x 260 "
+                                    "columns loaded per 512 cells of a row, same rhs / mask / store bytes — not more traffic")
 
     # ---- e2e: the same step through the C-ABI with HOST buffers (pinned): every step uploads its u, v, p and downloads
     # the u, v, p it produced.  One handle does that in series (H2D, kernels, D2H: the PCIe time of 2 x 3 fields is

@@ -118,10 +118,14 @@ static int build_metrics(ifx_solver* s, const double* xf, const double* yf) {
   return IFX_OK;
 }
 
-// columns per CTA tile of the sweep kernels (mode 0: Poisson, 2: predictor)
+// The general Poisson sweep runs its wide geometry (four columns per thread, kernels_v4.cu: IFX_PPE_NC2_WIDE) on a single
+// GPU and the narrow one on slabs.  The ONE place that decides: the grid (tile_grid) and the launch (enqueue_ppe_sweep)
+// both ask here.
+bool ifx::ppe_wide_tiles(const ifx_solver* s) { return s->opt.nranks == 1; }
+
+// columns per CTA tile of the sweep kernels (mode 0: Laplace sweep, 1: general Poisson sweep, 2: predictor)
 static int tile_cols_for(const ifx_solver* s, int mode) {
-  (void)s;
-  return v4_tile_cols(mode);
+  return v4_tile_cols(mode, mode == 1 && ppe_wide_tiles(s));
 }
 
 int ifx::rows_per_cta_for(const ifx_solver* s, int mode) {
@@ -896,6 +900,7 @@ int ifx::ensure_facemask(ifx_solver* s) {
 
 int ifx::enqueue_ppe_sweep(ifx_solver* s, PpeSweepArgs& a, dim3 grid, bool laplace_ref, bool write_res) {
   s->launches++;
+  a.wide = (!laplace_ref && ppe_wide_tiles(s)) ? 1 : 0;       // the geometry `grid` was sized for (tile_grid, mode 1)
   IFX_CUDA(s, ifx::launch_ppe_sweep_v4(a, grid, s->stream, laplace_ref, write_res));
   return IFX_OK;
 }
@@ -916,7 +921,7 @@ int ifx::run_ppe_loop(ifx_solver* s, ifx_step_stats* st, bool laplace_ref) {
   IFX_CUDA(s, cudaEventRecord(s->ev[2], s->stream));
   const int base = s->cur_p;
   const bool slabs = s->connected && s->opt.nranks > 1;
-  const int tw_ppe = v4_tile_cols(laplace_ref ? 0 : 1);
+  const int tw_ppe = tile_cols_for(s, pmode);
   if (laplace_ref) {
     // set_pressure_BC (PPESolver.cu:164); the ring is then carried through every sweep (:21)
     s->launches += 2;

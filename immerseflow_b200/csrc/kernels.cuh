@@ -65,6 +65,7 @@ struct PpeSweepArgs {
   ReduceCfg rc;
   int rows_per_cta;
   int force;
+  int wide;                           // general operator: four columns per thread / 512-column tiles (capi.cu: ppe_wide_tiles)
   int sor, sor_colour;                // red-black SOR half-sweep of the given colour instead of a Jacobi sweep
   double sor_omega;
   HaloCtx hx;
@@ -269,7 +270,7 @@ cudaError_t launch_ppe_sweep_v4(const PpeSweepArgs& a, dim3 grid, cudaStream_t s
 // 4 doubles per CTA
 cudaError_t launch_ppe_pair(const PpeSweepArgs& a, dim3 grid, cudaStream_t st);
 int pair_tile_cols();
-int v4_tile_cols(int mode /*0: Laplace, 1: general Poisson, 2: predictor*/);
+int v4_tile_cols(int mode /*0: Laplace, 1: general Poisson, 2: predictor*/, bool wide = false /*mode 1: PpeSweepArgs::wide*/);
 // kernels_full.cu — PPE source term, projection, BC refresh (IFX_COMPAT_FULL)
 cudaError_t launch_apply_ring(const Layout& L, double* q, const double* two_bc, int neumann, cudaStream_t st);
 cudaError_t launch_faces_init(const Layout& L, const Metrics& M, const uint8_t* ct, const double* ub, const double* vb,

@@ -118,6 +118,7 @@ int fetch_small(ifx_solver* s, void* host_pinned, const void* dev, size_t bytes)
 int ensure_partials(ifx_solver* s, size_t nblocks);
 int ensure_exact_buffers(ifx_solver* s);
 int exact_decide(ifx_solver* s, const ReduceCfg& rc, bool two_arrays);
+bool ppe_wide_tiles(const ifx_solver* s);
 int rows_per_cta_for(const ifx_solver* s, int mode);
 dim3 tile_grid(const ifx_solver* s, int ry, int mode);
 double rounding_band(const ifx_solver* s, size_t nblocks, int rows_per_cta);

@@ -1,5 +1,5 @@
-"""Grid widths on and around the column-tile widths of the sweep kernels (256 for the predictor and the general Poisson sweep,
-512 for the Laplace sweep, 240 for the pair sweep): the last tile column then holds exactly one, all but one, or no inactive
+"""Grid widths on and around the column-tile widths of the sweep kernels (256 for the predictor and the slab geometry of the
+general Poisson sweep, 512 for its single-GPU geometry and for the Laplace sweep, 240 for the pair sweep): the last tile column then holds exactly one, all but one, or no inactive
 column — the guarded edge paths — and the result must equal the CPU oracle's bit for bit."""
 import numpy as np
 import pytest

@@ -1,6 +1,6 @@
 #!/bin/bash
 # Build a variant of the library with extra -D flags on the sweep-kernel TU (kernel experiments):
-#   tools/build_variant.sh NAME "-DIFX_EXP_SLEEP=100"   ->  tools/_bin/lib_NAME.so
+#   tools/build_variant.sh narrow "-DIFX_PPE_NC2_WIDE=1"   ->  tools/_bin/lib_narrow.so
 # Run it with IFX_LIBRARY=tools/_bin/lib_NAME.so python bench.py ...
 set -e
 cd "$(dirname "$0")/.."

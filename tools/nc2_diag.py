@@ -1,13 +1,17 @@
-"""Where does the four-columns-per-thread build of the general Poisson sweep (-DIFX_PPE_NC2=2) differ?
+"""The stage-release race of the TMA row pipeline, GPU against GPU over every cell (profiles/r2_nc2_race.md).
 
-The benchmark's first step (16384 x 16384, 8 moving lobed bodies, smooth non-zero starting pressure) is run in fresh
-processes, one library each (the default build and tools/_bin/lib_nc2.so), and the fields are compared GPU against GPU:
-a 64-bit xor fingerprint per (row, 256-column block) over the whole grid, and every cell of the row window the bench's
-own parity check looks at.  No torch, no oracle: the default build is bit-exact against the oracle at this scale in every
-bench run, so it is the reference here.  Output: gpurun_out/nc2_diag.json.
+The benchmark's steps (16384 x 16384, 8 moving lobed bodies, smooth non-zero starting pressure) are run in fresh processes,
+one library each, and u, v, p are compared through a 64-bit xor fingerprint per (row, 64-column block) over the whole grid.
+No torch, no oracle: the reference is the build every oracle comparison of round 2 was made with — two columns per thread
+in the general Poisson sweep, stage released right after the loads.  Output: gpurun_out/nc2_diag.json.
 
-    tools/build_variant.sh nc2 "-DIFX_PPE_NC2=2"           # here (cross-compiled)
-    gpurun -- python tools/nc2_diag.py                       # on the box
+    tools/build_variant.sh narrow_early "-DIFX_PPE_NC2_WIDE=1 -DIFX_RELEASE_EARLY=1"     # the reference (round-2 kernels)
+    tools/build_variant.sh narrow       "-DIFX_PPE_NC2_WIDE=1"                           # late release, two columns
+    tools/build_variant.sh wide_early   "-DIFX_RELEASE_EARLY=1"                          # the race
+    gpurun -- python tools/nc2_diag.py                                                   # the shipped library = wide, late
+
+(The runs on record used the same kernels under their earlier names: -DIFX_PPE_NC2=2 for the four-column geometry, which
+is now the single-GPU default; the hypothesis builds of r2_nc2_diag_variants.json are tools/experiments/kernels_v4_race_knobs.cu.txt.)
 """
 import json
 import os
@@ -112,16 +116,17 @@ def main():
     long_steps = int(os.environ.get("NC2_DIAG_LONG_STEPS", "10"))
     bin_ = os.path.join(ROOT, "tools", "_bin")
     # (tag, library, steps, mode, compared with): "ref" = the stage release of rounds 1-2 with two columns per thread, the
-    # build every oracle comparison of the round was made with
+    # build every oracle comparison of the round was made with.  (In r2_nc2_diag_release.json the same builds are called
+    # ref / new = narrow_late / nc2_late = shipped / nc2_early = wide_early.)
     lib = lambda n: os.path.join(bin_, f"lib_{n}.so")
-    plan = [("ref", lib("nc1_early"), long_steps, "jacobi", None),
-            ("new", "", long_steps, "jacobi", "ref"),                  # the shipped library: late release, two columns
-            ("nc2_late", lib("nc2"), long_steps, "jacobi", "ref"),     # late release, four columns
-            ("nc2_early", lib("nc2_early"), 1, "jacobi", "ref"),       # control: the race, on this box
-            ("new_pairs", "", 1, "pairs", "ref"),                      # two sweeps per pass (kernels_pair.cu), same iterates
-            ("ref_mg", lib("nc1_early"), 1, "mg", None),
-            ("new_mg", "", 1, "mg", "ref_mg"),
-            ("nc2_late_mg", lib("nc2"), 1, "mg", "ref_mg")]
+    plan = [("ref", lib("narrow_early"), long_steps, "jacobi", None),
+            ("shipped", "", long_steps, "jacobi", "ref"),                   # late release, four columns on a single GPU
+            ("narrow_late", lib("narrow"), long_steps, "jacobi", "ref"),    # late release, two columns (the slab geometry)
+            ("wide_early", lib("wide_early"), 1, "jacobi", "ref"),          # control: the race, on this box
+            ("shipped_pairs", "", 1, "pairs", "ref"),                       # two sweeps per pass (kernels_pair.cu), same iterates
+            ("ref_mg", lib("narrow_early"), 1, "mg", None),
+            ("shipped_mg", "", 1, "mg", "ref_mg"),
+            ("narrow_late_mg", lib("narrow"), 1, "mg", "ref_mg")]
     only = os.environ.get("NC2_DIAG_ONLY")
     if only:
         plan = [q for q in plan if q[0] in only.split(",")]

@@ -4,7 +4,8 @@ multiple of the tile width (edge tiles), the reference-order reduction (residual
 that stop the loops early.  Both libraries run the same cases in their own process; u, v, p must be equal in every bit
 after every step.  No torch, no oracle.  Output: gpurun_out/release_check.json.
 
-    gpurun -- python tools/release_check.py      (needs tools/_bin/lib_nc1_early.so: -DIFX_RELEASE_EARLY=1)
+    gpurun -- python tools/release_check.py      (needs tools/_bin/lib_narrow_early.so: tools/build_variant.sh narrow_early
+    "-DIFX_PPE_NC2_WIDE=1 -DIFX_RELEASE_EARLY=1"; the run on record compared the two-column geometry both ways)
 """
 import hashlib
 import json
@@ -68,7 +69,7 @@ def main():
         return child()
     t0 = time.time()
     res = {}
-    for tag, lib in (("early", os.path.join(ROOT, "tools", "_bin", "lib_nc1_early.so")), ("late", "")):
+    for tag, lib in (("early", os.path.join(ROOT, "tools", "_bin", "lib_narrow_early.so")), ("late", "")):
         env = dict(os.environ)
         env.pop("IFX_LIBRARY", None)
         if lib:
